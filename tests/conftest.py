@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import json
+
+    g = os.path.join(ROOT, "tests", "golden")
+    with open(os.path.join(g, "reference_kats.json")) as f:
+        kats = json.load(f)
+    with open(os.path.join(g, "poseidon_params.json")) as f:
+        params = json.load(f)
+    return {"kats": kats, "params": params}
