@@ -1,0 +1,143 @@
+/*
+ * pcs.h -- C ABI of the B200 polynomial-commitment engine (libpcs.so).
+ *
+ * Drop-in boundary for ONE hot path of Lain-Iwakuro/Plonky2-Demo:
+ *     PolynomialBatch::from_values / from_coeffs      plonky2/src/fri/oracle.rs:43-98
+ *       = batched Goldilocks coset LDE                field/src/fft.rs:57-206, field/src/polynomial/mod.rs:201-295
+ *       + transpose / reverse_index_bits              plonky2/src/util/mod.rs:22-28, util/src/lib.rs:188-237
+ *       + MerkleTree::new (Poseidon)                  plonky2/src/hash/merkle_tree.rs:135-166
+ * The reference has no FFI: its boundary is the generic Rust API.  These entry points are what
+ * a Rust `-sys` crate binds so that the shim's from_values / from_coeffs / MerkleTree::new / get /
+ * prove forward here for F = GoldilocksField, H = PoseidonHash.
+ *
+ * Conventions
+ *   - Field elements are uint64_t.  GoldilocksField is #[repr(transparent)] over u64
+ *     (field/src/goldilocks_field.rs:23-25) so Vec<GoldilocksField> == const uint64_t*.
+ *     Inputs may be non-canonical (any u64); every output is canonical (< p).
+ *   - HashOut<F> == uint64_t[4] (plonky2/src/hash/hash_types.rs:22-24), Vec<HashOut> == flat u64[4n].
+ *   - All pointers are HOST pointers unless the PCS_DEVICE_PTRS flag is given or the name ends in _dev.
+ *   - Every function returns 0 on success or a negative pcs_status; pcs_last_error() has the text.
+ *     The reference panics on invalid input; the Rust shim turns non-zero into panic!() with the
+ *     reference's message.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with PCS_ERR_CUDA.
+ *   - One commit in flight per process (the reference's call sites are sequential:
+ *     plonk/prover.rs:145,212,260; circuit_builder.rs:1021).
+ */
+#ifndef PCS_H
+#define PCS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define PCS_API __attribute__((visibility("default")))
+#else
+#define PCS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PCS_OK = 0,
+    PCS_ERR_CUDA = -1,         /* CUDA runtime error (incl. "no device")                                  */
+    PCS_ERR_NOT_POW2 = -2,     /* "Not a power of two: {n}"                       util/src/lib.rs:37      */
+    PCS_ERR_CAP_HEIGHT = -3,   /* "cap_height={} should be at most log2(leaves.len())={}" merkle_tree.rs:136-142 */
+    PCS_ERR_ALLOC = -4,
+    PCS_ERR_ARG = -5,          /* empty batch (oracle.rs:76 polynomials[0]), unequal lengths (oracle.rs:114), NULL */
+    PCS_ERR_TWO_ADICITY = -6,  /* log2(N) > 32                                    field/src/types.rs:269  */
+    PCS_ERR_NOT_INIT = -7
+} pcs_status;
+
+enum {
+    PCS_DEVICE_PTRS = 1u << 0,   /* input polynomial pointers are device pointers (no H2D copy)         */
+    PCS_KEEP_COEFFS = 1u << 1,   /* keep the coefficient vectors on the device (PolynomialBatch.polynomials) */
+    PCS_NO_LDE_STORE = 1u << 2   /* reserved                                                            */
+};
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* Select the CUDA device this process commits on and create the engine's stream.
+ * `stream` may be NULL (the engine creates its own) or an existing cudaStream_t the caller owns
+ * (e.g. torch's current stream) so that caller-side CUDA events time the engine's kernels. */
+PCS_API int pcs_init(int device, void* stream);
+PCS_API void pcs_shutdown(void);
+PCS_API const char* pcs_last_error(void);
+/* The cudaStream_t all engine work is enqueued on. */
+PCS_API void* pcs_stream(void);
+PCS_API int pcs_synchronize(void);
+
+/* ---- primitives (unit-testable against the reference's own tests) ------------------------------ */
+/* Poseidon::poseidon on n states, in place.                      plonky2/src/hash/poseidon.rs:599-609 */
+PCS_API int pcs_poseidon_permute(uint64_t* states /*[n][12]*/, size_t n);
+/* Hasher::hash_or_noop on n rows of `len` elements.               plonky2/src/plonk/config.rs:55-66   */
+PCS_API int pcs_hash_or_noop(const uint64_t* rows /*[n][len]*/, size_t n, size_t len, uint64_t* out /*[n][4]*/);
+/* PoseidonHash::two_to_one = compress.                            plonky2/src/hash/hashing.rs:98-115  */
+PCS_API int pcs_two_to_one(const uint64_t* left /*[n][4]*/, const uint64_t* right /*[n][4]*/, size_t n, uint64_t* out);
+/* fft_with_options(.., None, ..) / ifft_with_options on w polynomials, natural order in and out.
+ *                                                                 field/src/fft.rs:57-65, 72-95       */
+PCS_API int pcs_ntt(uint64_t* polys /*[w][n] in/out*/, size_t w, unsigned lg_n, int inverse);
+/* PolynomialBatch::lde_values (no salts): p.lde(rate_bits).coset_fft_with_options(shift, Some(rate_bits), ..)
+ * for every polynomial.                                           plonky2/src/fri/oracle.rs:100-118
+ * layout 0: out[w][N] natural order (== the reference's Vec<Vec<F>>);
+ * layout 1: out[N][w] leaf order (== transpose + reverse_index_bits_in_place, oracle.rs:83-84).       */
+PCS_API int pcs_coset_lde(const uint64_t* const* coeffs /*w pointers, d elements each*/, size_t w, unsigned lg_d,
+                  unsigned rate_bits, uint64_t shift, uint64_t* out, int layout);
+/* MerkleTree::new(leaves, cap_height).                            plonky2/src/hash/merkle_tree.rs:135-166
+ * leaves row-major [n][len]; digests [2(n - 2^cap_height)][4] in the reference's interleaved layout
+ * (merkle_tree.rs:43-51); cap [2^cap_height][4].                                                      */
+PCS_API int pcs_merkle_build(const uint64_t* leaves, size_t n, size_t len, unsigned cap_height, uint64_t* digests,
+                     uint64_t* cap);
+
+/* ---- the fused hot path ------------------------------------------------------------------------- */
+/* Opaque device-resident PolynomialBatch: coefficients (optional), LDE in leaf order (poly-major),
+ * digests and cap all stay in HBM; the accessors below serve the reference's consumers. */
+typedef struct pcs_batch pcs_batch;
+
+/* PolynomialBatch::from_coeffs(polynomials, rate_bits, blinding, cap_height, ..)  oracle.rs:68-98.
+ *   polys   : w pointers to d = 2^lg_d coefficients each (all the same length, oracle.rs:114)
+ *   salts   : NULL, or salt_w pointers to N = d << rate_bits elements each -- the reference draws
+ *             SALT_SIZE = 4 columns from OsRng when `blinding` (oracle.rs:26,119-123); the caller
+ *             supplies them so that the commitment is reproducible.
+ *   cap_out : NULL or [2^cap_height][4] host buffer, filled before return (the only D2H copy).
+ * With PCS_DEVICE_PTRS the call is asynchronous on pcs_stream() unless cap_out != NULL.           */
+PCS_API int pcs_commit_from_coeffs(const uint64_t* const* polys, size_t w, unsigned lg_d, unsigned rate_bits,
+                           unsigned cap_height, const uint64_t* const* salts, size_t salt_w, unsigned flags,
+                           uint64_t* cap_out, pcs_batch** out);
+/* PolynomialBatch::from_values: IFFT every column first.                         oracle.rs:43-65
+ *   coeffs_out : NULL, or w host pointers receiving the d coefficients of each polynomial
+ *                (the reference keeps them as `polynomials`).                                      */
+PCS_API int pcs_commit_from_values(const uint64_t* const* values, size_t w, unsigned lg_d, unsigned rate_bits,
+                           unsigned cap_height, const uint64_t* const* salts, size_t salt_w, unsigned flags,
+                           uint64_t* const* coeffs_out, uint64_t* cap_out, pcs_batch** out);
+
+/* Shape of a batch: n_leaves = N, leaf_len = w + salt_w, n_digests = 2 (N - 2^cap_height). */
+PCS_API int pcs_batch_shape(const pcs_batch* b, size_t* n_leaves, size_t* leaf_len, size_t* n_digests, unsigned* cap_height);
+/* merkle_tree.cap                                                                                   */
+PCS_API int pcs_batch_cap(const pcs_batch* b, uint64_t* cap /*[2^cap_height][4]*/);
+/* merkle_tree.digests (reference layout)                                                            */
+PCS_API int pcs_batch_digests(const pcs_batch* b, uint64_t* digests /*[n_digests][4]*/);
+/* merkle_tree.leaves[first .. first+count) as row-major [count][leaf_len] (transposed on the device). */
+PCS_API int pcs_batch_leaves(const pcs_batch* b, size_t first, size_t count, uint64_t* rows);
+/* MerkleTree::get for many indices at once (merkle_tree.rs:168); get_lde_values(i, step) is
+ * leaf index reverse_bits(i*step, log2 N) minus the salt columns (oracle.rs:128-133).              */
+PCS_API int pcs_batch_get_rows(const pcs_batch* b, const uint64_t* leaf_indices, size_t n, uint64_t* rows /*[n][leaf_len]*/);
+/* MerkleTree::prove(leaf_index): siblings bottom-up, [log2 N - cap_height][4].  merkle_tree.rs:173-207 */
+PCS_API int pcs_batch_prove(const pcs_batch* b, size_t leaf_index, uint64_t* siblings);
+/* polynomials[i].coeffs (needs PCS_KEEP_COEFFS or from_values).                                     */
+PCS_API int pcs_batch_coeffs(const pcs_batch* b, size_t poly, uint64_t* coeffs /*[d]*/);
+/* Device views (valid until pcs_batch_free): LDE is [leaf_len][N] poly-major in leaf order.        */
+PCS_API const uint64_t* pcs_batch_lde_dev(const pcs_batch* b);
+PCS_API const uint64_t* pcs_batch_digests_dev(const pcs_batch* b);
+PCS_API const uint64_t* pcs_batch_cap_dev(const pcs_batch* b);
+/* Wall-clock of the last commit's phases in ms, measured with CUDA events on pcs_stream():
+ * [0] "IFFT"  [1] "FFT + blinding"  [2] "transpose LDEs" (always 0: fused away)
+ * [3] leaf hashing  [4] node levels   ([3]+[4] = "build Merkle tree")   -- TimingTree scopes, oracle.rs:51-89.
+ * Synchronises the stream.                                                                         */
+PCS_API int pcs_batch_timings(const pcs_batch* b, float ms[5]);
+PCS_API void pcs_batch_free(pcs_batch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCS_H */

@@ -1,0 +1,502 @@
+// C ABI (include/pcs.h) of the polynomial-commitment engine: context, the fused
+// PolynomialBatch::from_coeffs / from_values path (plonky2/src/fri/oracle.rs:43-98) and the
+// accessors the reference's consumers need.  No CPU fallback anywhere in this file.
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pcs {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+struct Ctx {
+    bool init = false;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+};
+static Ctx g_ctx;
+
+static int fail(int code, const std::string& msg) {
+    set_error(msg);
+    return code;
+}
+
+#define PCS_NEED_INIT()                                                            \
+    do {                                                                           \
+        if (!g_ctx.init) {                                                         \
+            int _rc = pcs_init(-1, nullptr);                                       \
+            if (_rc) return _rc;                                                   \
+        }                                                                          \
+    } while (0)
+
+// stream-ordered temporary buffer
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    cudaError_t alloc(size_t bytes, cudaStream_t s) {
+        st = s;
+        return cudaMallocAsync(&p, bytes ? bytes : 8, s);
+    }
+    uint64_t* u64() { return (uint64_t*)p; }
+    void release() {
+        if (p) cudaFreeAsync(p, st);
+        p = nullptr;
+    }
+    ~DevBuf() { release(); }
+};
+
+}  // namespace pcs
+
+using namespace pcs;
+
+struct pcs_batch {
+    size_t w = 0, salt_w = 0;
+    unsigned lg_d = 0, rate_bits = 0, cap_height = 0;
+    size_t n = 0;          // N = d << rate_bits
+    size_t n_digests = 0;  // 2 (N - 2^cap)
+    uint64_t* coeffs = nullptr;   // [w][d] or null
+    uint64_t* lde = nullptr;      // [w + salt_w][N], leaf order
+    uint64_t* digests = nullptr;  // [n_digests][4]
+    uint64_t* cap = nullptr;      // [2^cap][4]
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool has_ifft = false;
+};
+
+extern "C" {
+
+const char* pcs_last_error(void) { return g_err.c_str(); }
+
+int pcs_init(int device, void* stream) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(PCS_ERR_CUDA, std::string("no CUDA device: the engine has no CPU fallback (") +
+                                      cudaGetErrorString(e) + ")");
+    if (device < 0) {
+        if (g_ctx.init) return PCS_OK;
+        device = 0;
+    }
+    if (g_ctx.init && (g_ctx.device != device)) pcs_shutdown();
+    PCS_CUDA(cudaSetDevice(device));
+    if (g_ctx.init) {
+        // re-bind the stream only
+        if (stream && stream != (void*)g_ctx.stream) {
+            if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.stream);
+            g_ctx.stream = (cudaStream_t)stream;
+            g_ctx.own_stream = false;
+        }
+        return PCS_OK;
+    }
+    g_ctx.device = device;
+    if (stream) {
+        g_ctx.stream = (cudaStream_t)stream;
+        g_ctx.own_stream = false;
+    } else {
+        PCS_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+        g_ctx.own_stream = true;
+    }
+    // keep freed blocks cached in the pool: commits reuse multi-GB buffers
+    cudaMemPool_t pool;
+    PCS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    PCS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    g_ctx.init = true;
+    return PCS_OK;
+}
+
+void pcs_shutdown(void) {
+    if (!g_ctx.init) return;
+    cudaStreamSynchronize(g_ctx.stream);
+    ntt_plans_free();
+    if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.stream);
+    g_ctx = Ctx();
+}
+
+void* pcs_stream(void) { return g_ctx.init ? (void*)g_ctx.stream : nullptr; }
+
+int pcs_synchronize(void) {
+    PCS_NEED_INIT();
+    PCS_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return PCS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// primitives
+// ------------------------------------------------------------------------------------------------
+int pcs_poseidon_permute(uint64_t* states, size_t n) {
+    PCS_NEED_INIT();
+    if (n == 0) return PCS_OK;
+    if (!states) return fail(PCS_ERR_ARG, "states is NULL");
+    cudaStream_t st = g_ctx.stream;
+    DevBuf d;
+    PCS_CUDA(d.alloc(n * 12 * 8, st));
+    PCS_CUDA(cudaMemcpyAsync(d.p, states, n * 12 * 8, cudaMemcpyHostToDevice, st));
+    PCS_CUDA(launch_permute(d.u64(), n, st));
+    PCS_CUDA(cudaMemcpyAsync(states, d.p, n * 12 * 8, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+int pcs_hash_or_noop(const uint64_t* rows, size_t n, size_t len, uint64_t* out) {
+    PCS_NEED_INIT();
+    if (n == 0) return PCS_OK;
+    if (!rows || !out) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (len == 0) {  // hash_or_noop of an empty slice: all-zero HashOut (config.rs:56-62)
+        memset(out, 0, n * 32);
+        return PCS_OK;
+    }
+    cudaStream_t st = g_ctx.stream;
+    DevBuf d_rows, d_cols, d_out;
+    PCS_CUDA(d_rows.alloc(n * len * 8, st));
+    PCS_CUDA(d_cols.alloc(n * len * 8, st));
+    PCS_CUDA(d_out.alloc(n * 32, st));
+    PCS_CUDA(cudaMemcpyAsync(d_rows.p, rows, n * len * 8, cudaMemcpyHostToDevice, st));
+    PCS_CUDA(launch_transpose(d_rows.u64(), len, d_cols.u64(), n, n, len, st));
+    PCS_CUDA(launch_hash_cols_plain(d_cols.u64(), n, (uint32_t)len, n, d_out.u64(), st));
+    PCS_CUDA(cudaMemcpyAsync(out, d_out.p, n * 32, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+int pcs_two_to_one(const uint64_t* left, const uint64_t* right, size_t n, uint64_t* out) {
+    PCS_NEED_INIT();
+    if (n == 0) return PCS_OK;
+    if (!left || !right || !out) return fail(PCS_ERR_ARG, "NULL pointer");
+    cudaStream_t st = g_ctx.stream;
+    DevBuf l, r, o;
+    PCS_CUDA(l.alloc(n * 32, st));
+    PCS_CUDA(r.alloc(n * 32, st));
+    PCS_CUDA(o.alloc(n * 32, st));
+    PCS_CUDA(cudaMemcpyAsync(l.p, left, n * 32, cudaMemcpyHostToDevice, st));
+    PCS_CUDA(cudaMemcpyAsync(r.p, right, n * 32, cudaMemcpyHostToDevice, st));
+    PCS_CUDA(launch_two_to_one(l.u64(), r.u64(), n, o.u64(), st));
+    PCS_CUDA(cudaMemcpyAsync(out, o.p, n * 32, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+int pcs_ntt(uint64_t* polys, size_t w, unsigned lg_n, int inverse) {
+    PCS_NEED_INIT();
+    if (w == 0) return PCS_OK;
+    if (!polys) return fail(PCS_ERR_ARG, "polys is NULL");
+    if (lg_n > 32) return fail(PCS_ERR_TWO_ADICITY, "n_log <= TWO_ADICITY violated");
+    cudaStream_t st = g_ctx.stream;
+    size_t n = (size_t)1 << lg_n;
+    NttPlan* plan = ntt_plan_get(lg_n, 0, inverse != 0, 1, st);
+    if (!plan) return fail(PCS_ERR_ALLOC, "twiddle table allocation failed");
+    DevBuf a, b;
+    PCS_CUDA(a.alloc(w * n * 8, st));
+    PCS_CUDA(b.alloc(w * n * 8, st));
+    PCS_CUDA(cudaMemcpyAsync(a.p, polys, w * n * 8, cudaMemcpyHostToDevice, st));
+    PCS_CUDA(ntt_lde(plan, a.u64(), n, b.u64(), n, w, st));            // natural -> bit-reversed
+    PCS_CUDA(launch_bitrev_permute(b.u64(), n, a.u64(), n, w, lg_n, st));  // -> natural
+    PCS_CUDA(cudaMemcpyAsync(polys, a.p, w * n * 8, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+// gather w separately allocated host/device polynomials into one [w][d] device matrix
+static int stage_polys(const uint64_t* const* polys, size_t w, size_t d, bool device_ptrs, uint64_t* dst,
+                       cudaStream_t st) {
+    for (size_t j = 0; j < w; j++) {
+        if (!polys[j]) return fail(PCS_ERR_ARG, "NULL polynomial pointer");
+        PCS_CUDA(cudaMemcpyAsync(dst + j * d, polys[j], d * 8, device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    }
+    return PCS_OK;
+}
+
+int pcs_coset_lde(const uint64_t* const* coeffs, size_t w, unsigned lg_d, unsigned rate_bits, uint64_t shift,
+                  uint64_t* out, int layout) {
+    PCS_NEED_INIT();
+    if (w == 0) return fail(PCS_ERR_ARG, "empty batch (oracle.rs:103 polynomials[0])");
+    if (!coeffs || !out) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (lg_d + rate_bits > 32) return fail(PCS_ERR_TWO_ADICITY, "n_log <= TWO_ADICITY violated");
+    cudaStream_t st = g_ctx.stream;
+    size_t d = (size_t)1 << lg_d, n = d << rate_bits;
+    NttPlan* plan = ntt_plan_get(lg_d, rate_bits, false, shift, st);
+    if (!plan) return fail(PCS_ERR_ALLOC, "twiddle table allocation failed");
+    DevBuf c, lde, o;
+    PCS_CUDA(c.alloc(w * d * 8, st));
+    PCS_CUDA(lde.alloc(w * n * 8, st));
+    PCS_CUDA(o.alloc(w * n * 8, st));
+    int rc = stage_polys(coeffs, w, d, false, c.u64(), st);
+    if (rc) return rc;
+    PCS_CUDA(ntt_lde(plan, c.u64(), d, lde.u64(), n, w, st));
+    if (layout == 0)
+        PCS_CUDA(launch_bitrev_permute(lde.u64(), n, o.u64(), n, w, lg_d + rate_bits, st));
+    else
+        PCS_CUDA(launch_transpose(lde.u64(), n, o.u64(), w, w, n, st));
+    PCS_CUDA(cudaMemcpyAsync(out, o.p, w * n * 8, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+// leaf digests + all node levels; cols = [width][n] poly-major
+static int build_tree_dev(const uint64_t* cols, size_t n, size_t width, unsigned lg_n, unsigned cap_height,
+                          uint64_t* digests, uint64_t* cap, cudaStream_t st, cudaEvent_t after_leaves) {
+    unsigned lg_sub = lg_n - cap_height;
+    PCS_CUDA(launch_leaf_hash_cols(cols, n, (uint32_t)width, n, lg_sub, digests, cap, st));
+    if (after_leaves) PCS_CUDA(cudaEventRecord(after_leaves, st));
+    for (unsigned level = 1; level <= lg_sub; level++)
+        PCS_CUDA(launch_node_level(digests, cap, lg_sub, level, n >> level, st));
+    return PCS_OK;
+}
+
+int pcs_merkle_build(const uint64_t* leaves, size_t n, size_t len, unsigned cap_height, uint64_t* digests,
+                     uint64_t* cap) {
+    PCS_NEED_INIT();
+    int lg_n = ilog2_strict(n);
+    if (lg_n < 0) return fail(PCS_ERR_NOT_POW2, "Not a power of two: " + std::to_string(n));
+    if ((int)cap_height > lg_n)
+        return fail(PCS_ERR_CAP_HEIGHT, "cap_height=" + std::to_string(cap_height) +
+                                            " should be at most log2(leaves.len())=" + std::to_string(lg_n));
+    if (!leaves || !cap || len == 0) return fail(PCS_ERR_ARG, "NULL pointer or empty leaves");
+    cudaStream_t st = g_ctx.stream;
+    size_t n_cap = (size_t)1 << cap_height, n_dig = 2 * (n - n_cap);
+    if (n_dig && !digests) return fail(PCS_ERR_ARG, "digests is NULL");
+    DevBuf d_rows, d_cols, d_dig, d_cap;
+    PCS_CUDA(d_rows.alloc(n * len * 8, st));
+    PCS_CUDA(d_cols.alloc(n * len * 8, st));
+    PCS_CUDA(d_dig.alloc(n_dig * 32, st));
+    PCS_CUDA(d_cap.alloc(n_cap * 32, st));
+    PCS_CUDA(cudaMemcpyAsync(d_rows.p, leaves, n * len * 8, cudaMemcpyHostToDevice, st));
+    PCS_CUDA(launch_transpose(d_rows.u64(), len, d_cols.u64(), n, n, len, st));
+    int rc = build_tree_dev(d_cols.u64(), n, len, (unsigned)lg_n, cap_height, d_dig.u64(), d_cap.u64(), st, nullptr);
+    if (rc) return rc;
+    if (n_dig) PCS_CUDA(cudaMemcpyAsync(digests, d_dig.p, n_dig * 32, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaMemcpyAsync(cap, d_cap.p, n_cap * 32, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused hot path
+// ------------------------------------------------------------------------------------------------
+void pcs_batch_free(pcs_batch* b) {
+    if (!b) return;
+    cudaStream_t st = g_ctx.stream;
+    if (b->coeffs) cudaFreeAsync(b->coeffs, st);
+    if (b->lde) cudaFreeAsync(b->lde, st);
+    if (b->digests) cudaFreeAsync(b->digests, st);
+    if (b->cap) cudaFreeAsync(b->cap, st);
+    for (auto& e : b->ev)
+        if (e) cudaEventDestroy(e);
+    delete b;
+}
+
+static int commit_common(const uint64_t* const* polys, bool from_values, size_t w, unsigned lg_d, unsigned rate_bits,
+                         unsigned cap_height, const uint64_t* const* salts, size_t salt_w, unsigned flags,
+                         uint64_t* const* coeffs_out, uint64_t* cap_out, pcs_batch** out) {
+    PCS_NEED_INIT();
+    if (!out) return fail(PCS_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (w == 0 || !polys) return fail(PCS_ERR_ARG, "empty batch (oracle.rs:76 polynomials[0])");
+    if (salt_w && !salts) return fail(PCS_ERR_ARG, "salts is NULL");
+    unsigned lg_n = lg_d + rate_bits;
+    if (lg_n > 32) return fail(PCS_ERR_TWO_ADICITY, "n_log <= TWO_ADICITY violated");
+    if (cap_height > lg_n)
+        return fail(PCS_ERR_CAP_HEIGHT, "cap_height=" + std::to_string(cap_height) +
+                                            " should be at most log2(leaves.len())=" + std::to_string(lg_n));
+    cudaStream_t st = g_ctx.stream;
+    const bool dev_ptrs = flags & PCS_DEVICE_PTRS;
+    const size_t d = (size_t)1 << lg_d, n = d << rate_bits, wt = w + salt_w;
+    const size_t n_cap = (size_t)1 << cap_height;
+
+    NttPlan* plan = ntt_plan_get(lg_d, rate_bits, false, 7 /* F::coset_shift(), types.rs:437 */, st);
+    NttPlan* iplan = from_values ? ntt_plan_get(lg_d, 0, true, 1, st) : nullptr;
+    if (!plan || (from_values && !iplan)) return fail(PCS_ERR_ALLOC, "twiddle table allocation failed");
+
+    pcs_batch* b = new pcs_batch();
+    b->w = w; b->salt_w = salt_w; b->lg_d = lg_d; b->rate_bits = rate_bits; b->cap_height = cap_height;
+    b->n = n; b->n_digests = 2 * (n - n_cap); b->has_ifft = from_values;
+    struct Guard { pcs_batch* b; bool armed = true; ~Guard() { if (armed) pcs_batch_free(b); } } guard{b};
+    for (auto& e : b->ev) PCS_CUDA(cudaEventCreate(&e));
+    PCS_CUDA(cudaMallocAsync((void**)&b->lde, wt * n * 8, st));
+    PCS_CUDA(cudaMallocAsync((void**)&b->digests, b->n_digests ? b->n_digests * 32 : 32, st));
+    PCS_CUDA(cudaMallocAsync((void**)&b->cap, n_cap * 32, st));
+
+    // ---- inputs -> one contiguous [w][d] device matrix ----
+    bool contiguous_dev = dev_ptrs;
+    if (dev_ptrs)
+        for (size_t j = 0; j < w; j++) contiguous_dev = contiguous_dev && polys[j] == polys[0] + j * d;
+    const uint64_t* src = nullptr;   // [w][d] device input (values or coefficients)
+    uint64_t* staged = nullptr;
+    if (contiguous_dev && !from_values && !(flags & PCS_KEEP_COEFFS)) {
+        src = polys[0];
+    } else {
+        PCS_CUDA(cudaMallocAsync((void**)&staged, w * d * 8, st));
+        b->coeffs = staged;  // owned by the batch from here on
+        if (contiguous_dev)
+            PCS_CUDA(cudaMemcpyAsync(staged, polys[0], w * d * 8, cudaMemcpyDeviceToDevice, st));
+        else {
+            int rc = stage_polys(polys, w, d, dev_ptrs, staged, st);
+            if (rc) return rc;
+        }
+        src = staged;
+    }
+    PCS_CUDA(cudaEventRecord(b->ev[0], st));
+
+    // ---- "IFFT" (oracle.rs:51-55) ----
+    if (from_values) {
+        // values (natural) -> coefficients in bit-reversed order (scratch = head of the LDE buffer)
+        PCS_CUDA(ntt_inverse_bitrev(iplan, src, d, b->lde, d, w, st));
+        PCS_CUDA(launch_bitrev_permute(b->lde, d, staged, d, w, lg_d, st));  // -> natural order, in `staged`
+        if (coeffs_out)
+            for (size_t j = 0; j < w; j++)
+                if (coeffs_out[j])
+                    PCS_CUDA(cudaMemcpyAsync(coeffs_out[j], staged + j * d, d * 8, cudaMemcpyDeviceToHost, st));
+    }
+    PCS_CUDA(cudaEventRecord(b->ev[1], st));
+
+    // ---- "FFT + blinding" (oracle.rs:100-125), output already in leaf order ----
+    PCS_CUDA(ntt_lde(plan, src, d, b->lde, n, w, st));
+    for (size_t k = 0; k < salt_w; k++) {
+        if (!salts[k]) return fail(PCS_ERR_ARG, "NULL salt pointer");
+        // the caller's salt column k is in natural LDE order like lde_values (oracle.rs:119-123);
+        // leaf order = bit-reversed rows (oracle.rs:84)
+        DevBuf tmp;
+        PCS_CUDA(tmp.alloc(n * 8, st));
+        PCS_CUDA(cudaMemcpyAsync(tmp.p, salts[k], n * 8, dev_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        PCS_CUDA(launch_canonicalize(tmp.u64(), n, st));
+        PCS_CUDA(launch_bitrev_permute(tmp.u64(), n, b->lde + (w + k) * n, n, 1, lg_n, st));
+    }
+    PCS_CUDA(cudaEventRecord(b->ev[2], st));
+    // "transpose LDEs" (oracle.rs:83): fused away -- the hash kernel reads columns directly
+    PCS_CUDA(cudaEventRecord(b->ev[3], st));
+
+    // ---- "build Merkle tree" (oracle.rs:85-89) ----
+    int rc = build_tree_dev(b->lde, n, wt, lg_n, cap_height, b->digests, b->cap, st, b->ev[4]);
+    if (rc) return rc;
+    PCS_CUDA(cudaEventRecord(b->ev[5], st));
+
+    if (b->coeffs && !from_values && !(flags & PCS_KEEP_COEFFS)) {
+        cudaFreeAsync(b->coeffs, st);
+        b->coeffs = nullptr;
+    }
+    if (cap_out) {
+        PCS_CUDA(cudaMemcpyAsync(cap_out, b->cap, n_cap * 32, cudaMemcpyDeviceToHost, st));
+        PCS_CUDA(cudaStreamSynchronize(st));
+    } else if (!dev_ptrs) {
+        PCS_CUDA(cudaStreamSynchronize(st));  // host inputs must not be reused before the copies finish
+    }
+    guard.armed = false;
+    *out = b;
+    return PCS_OK;
+}
+
+int pcs_commit_from_coeffs(const uint64_t* const* polys, size_t w, unsigned lg_d, unsigned rate_bits,
+                           unsigned cap_height, const uint64_t* const* salts, size_t salt_w, unsigned flags,
+                           uint64_t* cap_out, pcs_batch** out) {
+    return commit_common(polys, false, w, lg_d, rate_bits, cap_height, salts, salt_w, flags, nullptr, cap_out, out);
+}
+
+int pcs_commit_from_values(const uint64_t* const* values, size_t w, unsigned lg_d, unsigned rate_bits,
+                           unsigned cap_height, const uint64_t* const* salts, size_t salt_w, unsigned flags,
+                           uint64_t* const* coeffs_out, uint64_t* cap_out, pcs_batch** out) {
+    return commit_common(values, true, w, lg_d, rate_bits, cap_height, salts, salt_w, flags, coeffs_out, cap_out, out);
+}
+
+int pcs_batch_shape(const pcs_batch* b, size_t* n_leaves, size_t* leaf_len, size_t* n_digests, unsigned* cap_height) {
+    if (!b) return fail(PCS_ERR_ARG, "batch is NULL");
+    if (n_leaves) *n_leaves = b->n;
+    if (leaf_len) *leaf_len = b->w + b->salt_w;
+    if (n_digests) *n_digests = b->n_digests;
+    if (cap_height) *cap_height = b->cap_height;
+    return PCS_OK;
+}
+
+int pcs_batch_cap(const pcs_batch* b, uint64_t* cap) {
+    if (!b || !cap) return fail(PCS_ERR_ARG, "NULL pointer");
+    cudaStream_t st = g_ctx.stream;
+    PCS_CUDA(cudaMemcpyAsync(cap, b->cap, ((size_t)32) << b->cap_height, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+int pcs_batch_digests(const pcs_batch* b, uint64_t* digests) {
+    if (!b) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (b->n_digests == 0) return PCS_OK;
+    if (!digests) return fail(PCS_ERR_ARG, "NULL pointer");
+    cudaStream_t st = g_ctx.stream;
+    PCS_CUDA(cudaMemcpyAsync(digests, b->digests, b->n_digests * 32, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+int pcs_batch_leaves(const pcs_batch* b, size_t first, size_t count, uint64_t* rows) {
+    if (!b || !rows) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (first + count > b->n) return fail(PCS_ERR_ARG, "leaf range out of bounds");
+    if (count == 0) return PCS_OK;
+    cudaStream_t st = g_ctx.stream;
+    size_t wt = b->w + b->salt_w;
+    // transpose in slabs so that the staging buffer stays small
+    const size_t slab = (size_t)1 << 20;
+    DevBuf tmp;
+    PCS_CUDA(tmp.alloc((count < slab ? count : slab) * wt * 8, st));
+    for (size_t off = 0; off < count; off += slab) {
+        size_t c = count - off < slab ? count - off : slab;
+        PCS_CUDA(launch_transpose(b->lde + first + off, b->n, tmp.u64(), wt, wt, c, st));
+        PCS_CUDA(cudaMemcpyAsync(rows + off * wt, tmp.p, c * wt * 8, cudaMemcpyDeviceToHost, st));
+    }
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+int pcs_batch_get_rows(const pcs_batch* b, const uint64_t* leaf_indices, size_t n, uint64_t* rows) {
+    if (!b || (n && (!leaf_indices || !rows))) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (n == 0) return PCS_OK;
+    for (size_t k = 0; k < n; k++)
+        if (leaf_indices[k] >= b->n) return fail(PCS_ERR_ARG, "leaf index out of bounds");
+    cudaStream_t st = g_ctx.stream;
+    size_t wt = b->w + b->salt_w;
+    DevBuf idx, o;
+    PCS_CUDA(idx.alloc(n * 8, st));
+    PCS_CUDA(o.alloc(n * wt * 8, st));
+    PCS_CUDA(cudaMemcpyAsync(idx.p, leaf_indices, n * 8, cudaMemcpyHostToDevice, st));
+    PCS_CUDA(launch_gather_rows(b->lde, b->n, (uint32_t)wt, idx.u64(), n, o.u64(), st));
+    PCS_CUDA(cudaMemcpyAsync(rows, o.p, n * wt * 8, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+int pcs_batch_prove(const pcs_batch* b, size_t leaf_index, uint64_t* siblings) {
+    if (!b) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (leaf_index >= b->n) return fail(PCS_ERR_ARG, "leaf index out of bounds");
+    unsigned lg_sub = b->lg_d + b->rate_bits - b->cap_height;
+    if (lg_sub == 0) return PCS_OK;
+    if (!siblings) return fail(PCS_ERR_ARG, "NULL pointer");
+    cudaStream_t st = g_ctx.stream;
+    DevBuf o;
+    PCS_CUDA(o.alloc(lg_sub * 32, st));
+    PCS_CUDA(launch_prove(b->digests, lg_sub, leaf_index, o.u64(), st));
+    PCS_CUDA(cudaMemcpyAsync(siblings, o.p, lg_sub * 32, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+int pcs_batch_coeffs(const pcs_batch* b, size_t poly, uint64_t* coeffs) {
+    if (!b || !coeffs) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (!b->coeffs) return fail(PCS_ERR_ARG, "coefficients were not kept (PCS_KEEP_COEFFS)");
+    if (poly >= b->w) return fail(PCS_ERR_ARG, "polynomial index out of bounds");
+    cudaStream_t st = g_ctx.stream;
+    size_t d = (size_t)1 << b->lg_d;
+    PCS_CUDA(cudaMemcpyAsync(coeffs, b->coeffs + poly * d, d * 8, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+const uint64_t* pcs_batch_lde_dev(const pcs_batch* b) { return b ? b->lde : nullptr; }
+const uint64_t* pcs_batch_digests_dev(const pcs_batch* b) { return b ? b->digests : nullptr; }
+const uint64_t* pcs_batch_cap_dev(const pcs_batch* b) { return b ? b->cap : nullptr; }
+
+int pcs_batch_timings(const pcs_batch* b, float ms[5]) {
+    if (!b || !ms) return fail(PCS_ERR_ARG, "NULL pointer");
+    PCS_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    for (int i = 0; i < 5; i++) PCS_CUDA(cudaEventElapsedTime(&ms[i], b->ev[i], b->ev[i + 1]));
+    return PCS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// Shared declarations for the polynomial-commitment engine (libpcs.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "pcs.h"
+
+namespace pcs {
+
+void set_error(const std::string& msg);
+
+#define PCS_CUDA(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            pcs::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+            return PCS_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+
+
+static inline int ilog2_strict(size_t n) {
+    if (n == 0 || (n & (n - 1))) return -1;
+    int r = 0;
+    while ((n >> r) != 1) r++;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// hash_kernels.cu
+// ------------------------------------------------------------------------------------------------
+// In-place Poseidon permutation of n states, row-major [n][12].
+cudaError_t launch_permute(uint64_t* states, size_t n, cudaStream_t st);
+// Leaf digests from a column-major (poly-major) matrix: element (leaf i, column j) at
+// cols[j*col_stride + i].  Digest of leaf i goes to its slot in the reference digest layout
+// (merkle_tree.rs:43-51) or into cap when the subtree is a single leaf.
+cudaError_t launch_leaf_hash_cols(const uint64_t* cols, size_t col_stride, uint32_t width, size_t n_leaves,
+                                  unsigned lg_sub /*log2 leaves per cap subtree*/, uint64_t* digests,
+                                  uint64_t* cap, cudaStream_t st);
+// Plain variant: digest i -> out[i*4..] (pcs_hash_or_noop)
+cudaError_t launch_hash_cols_plain(const uint64_t* cols, size_t col_stride, uint32_t width, size_t n,
+                                   uint64_t* out, cudaStream_t st);
+// One level of two_to_one: nodes of level `level` (1 = parents of leaf digests) for all subtrees.
+cudaError_t launch_node_level(uint64_t* digests, uint64_t* cap, unsigned lg_sub, unsigned level,
+                              size_t n_nodes /*total at this level*/, cudaStream_t st);
+cudaError_t launch_two_to_one(const uint64_t* l, const uint64_t* r, size_t n, uint64_t* out, cudaStream_t st);
+// Merkle path gather: siblings of leaf_index, bottom-up ([lg_sub][4]).
+cudaError_t launch_prove(const uint64_t* digests, unsigned lg_sub, size_t leaf_index, uint64_t* siblings,
+                         cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// ntt.cu
+// ------------------------------------------------------------------------------------------------
+struct NttPlan;  // twiddle tables for one (lg_d, rate_bits, direction, shift)
+NttPlan* ntt_plan_get(unsigned lg_d, unsigned rate_bits, bool inverse, uint64_t shift, cudaStream_t st);
+void ntt_plans_free();
+// Coset LDE: coeffs [w][d] (poly stride in_stride) -> out [w][N] (poly stride out_stride), leaf
+// (bit-reversed) order: out[j][c*d + t] = P_j(shift * w_N^{brev_r(c)} * w_d^{brev(t)}).
+cudaError_t ntt_lde(const NttPlan* plan, const uint64_t* coeffs, size_t in_stride, uint64_t* out,
+                    size_t out_stride, size_t w, cudaStream_t st);
+// Inverse NTT incl. 1/d scaling: values [w][d] natural order -> `out` in BIT-REVERSED order.
+cudaError_t ntt_inverse_bitrev(const NttPlan* plan, const uint64_t* values, size_t in_stride, uint64_t* out,
+                               size_t out_stride, size_t w, cudaStream_t st);
+// out[j][brev(i)] = in[j][i]
+cudaError_t launch_bitrev_permute(const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride,
+                                  size_t w, unsigned lg_n, cudaStream_t st);
+// out[c][r] = in[r][c] for in [rows][cols] (row pitch in_pitch), out row pitch out_pitch
+cudaError_t launch_transpose(const uint64_t* in, size_t in_pitch, uint64_t* out, size_t out_pitch,
+                             size_t rows, size_t cols, cudaStream_t st);
+// gather rows: out[k][j] = cols[j*col_stride + idx[k]]
+cudaError_t launch_gather_rows(const uint64_t* cols, size_t col_stride, uint32_t width, const uint64_t* idx,
+                               size_t n_idx, uint64_t* out, cudaStream_t st);
+cudaError_t launch_canonicalize(uint64_t* data, size_t n, cudaStream_t st);
+
+}  // namespace pcs

@@ -1,0 +1,61 @@
+// Sponge leaf hashing over poly-major (column-major) LDE data: one thread per leaf, every load
+// coalesced across the warp (thread i reads element i of each column).
+//
+// Reference: hash_or_noop (plonky2/src/plonk/config.rs:55-66) -> hash_n_to_m_no_pad
+// (plonky2/src/hash/hashing.rs:119-142): overwrite-mode sponge, rate 8, no padding; rows of <= 4
+// elements are copied (canonicalised, zero padded), not hashed.  Digests land directly in the
+// reference's interleaved layout (merkle_tree.rs:43-51), leaf level of fill_subtree (:69-96).
+//
+// Bound: integer pipes, NOT HBM: a 135-element leaf = 17 permutations per 1080 B read.
+#include "hash_common.cuh"
+
+namespace pcs {
+
+// tree_mode: digest of leaf i goes to its tree slot (or cap); otherwise to out[4*i].
+__global__ void __launch_bounds__(HASH_THREADS)
+k_hash_cols(const uint64_t* __restrict__ cols, size_t col_stride, uint32_t width, size_t n, int tree_mode,
+            unsigned lg_sub, uint64_t* __restrict__ digests, uint64_t* __restrict__ cap) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t d[4];
+    const uint64_t* p = cols + i;
+    if (width <= 4) {  // hash_or_noop: not hashed
+#pragma unroll
+        for (int k = 0; k < 4; k++) d[k] = (uint32_t)k < width ? gl::canon(p[(size_t)k * col_stride]) : 0;
+    } else {
+        uint64_t s[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) s[k] = 0;
+#pragma unroll 1
+        for (uint32_t j = 0; j < width; j += 8) {
+            // a short last chunk overwrites only the first (width - j) lanes (hashing.rs:128-131)
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (j + k < width) s[k] = gl::canon(__ldg(p + (size_t)(j + k) * col_stride));
+            poseidon12(s);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) d[k] = s[k];
+    }
+    uint64_t* slot = tree_mode ? digest_slot(digests, cap, lg_sub, 0, i) : digests + 4 * i;
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(slot);
+    o[0] = make_ulonglong2(d[0], d[1]);
+    o[1] = make_ulonglong2(d[2], d[3]);
+}
+
+cudaError_t launch_leaf_hash_cols(const uint64_t* cols, size_t col_stride, uint32_t width, size_t n_leaves,
+                                  unsigned lg_sub, uint64_t* digests, uint64_t* cap, cudaStream_t st) {
+    if (n_leaves == 0) return cudaSuccess;
+    k_hash_cols<<<grid_for(n_leaves, HASH_THREADS), HASH_THREADS, 0, st>>>(cols, col_stride, width, n_leaves, 1,
+                                                                          lg_sub, digests, cap);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hash_cols_plain(const uint64_t* cols, size_t col_stride, uint32_t width, size_t n,
+                                   uint64_t* out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_hash_cols<<<grid_for(n, HASH_THREADS), HASH_THREADS, 0, st>>>(cols, col_stride, width, n, 0, 0, out, nullptr);
+    return cudaGetLastError();
+}
+
+}  // namespace pcs

@@ -1,0 +1,78 @@
+// Merkle node levels (two_to_one) and path extraction.
+//
+// Reference: compress (plonky2/src/hash/hashing.rs:98-115): state = [l0..3, r0..3, 0,0,0,0],
+// permute, take 4.  fill_subtree (merkle_tree.rs:69-96) recurses with rayon::join; here each
+// tree level is one launch with one thread per node, writing into the reference digest layout.
+// prove(): merkle_tree.rs:173-207.
+#include "hash_common.cuh"
+
+namespace pcs {
+
+// tree_mode: node k of `level` from its two children in the tree layout.
+// plain mode: out[k] = two_to_one(l[k], r[k])  (a = l, b = r, out = c).
+__global__ void __launch_bounds__(HASH_THREADS)
+k_compress(uint64_t* __restrict__ a, uint64_t* __restrict__ b, uint64_t* __restrict__ c, int tree_mode,
+           unsigned lg_sub, unsigned level, size_t n) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const ulonglong2 *l, *r;
+    uint64_t* out;
+    if (tree_mode) {
+        // children 2k, 2k+1 of level-1 are stored side by side (64 contiguous bytes)
+        l = reinterpret_cast<const ulonglong2*>(digest_slot(a, b, lg_sub, level - 1, 2 * k));
+        r = l + 2;
+        out = digest_slot(a, b, lg_sub, level, k);
+    } else {
+        l = reinterpret_cast<const ulonglong2*>(a + 4 * k);
+        r = reinterpret_cast<const ulonglong2*>(b + 4 * k);
+        out = c + 4 * k;
+    }
+    uint64_t s[12];
+    ulonglong2 v0 = l[0], v1 = l[1], v2 = r[0], v3 = r[1];
+    s[0] = gl::canon(v0.x); s[1] = gl::canon(v0.y); s[2] = gl::canon(v1.x); s[3] = gl::canon(v1.y);
+    s[4] = gl::canon(v2.x); s[5] = gl::canon(v2.y); s[6] = gl::canon(v3.x); s[7] = gl::canon(v3.y);
+    s[8] = s[9] = s[10] = s[11] = 0;
+    poseidon12(s);
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(out);
+    o[0] = make_ulonglong2(s[0], s[1]);
+    o[1] = make_ulonglong2(s[2], s[3]);
+}
+
+// MerkleTree::prove: one thread per layer copies the sibling digest.
+__global__ void k_prove(const uint64_t* __restrict__ digests, unsigned lg_sub, size_t leaf_index,
+                        uint64_t* __restrict__ siblings) {
+    unsigned i = threadIdx.x;
+    if (i >= lg_sub) return;
+    size_t s = leaf_index >> lg_sub;
+    size_t q = leaf_index & (((size_t)1 << lg_sub) - 1);
+    size_t node = (q >> i) ^ 1;  // sibling at level i
+    size_t sub_len = 2 * (((size_t)1 << lg_sub) - 1);
+    size_t idx = 2 * (((node >> 1) << (i + 1)) + ((size_t)1 << i) - 1) + (node & 1);
+    const uint64_t* src = digests + (s * sub_len + idx) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) siblings[4 * i + k] = src[k];
+}
+
+cudaError_t launch_node_level(uint64_t* digests, uint64_t* cap, unsigned lg_sub, unsigned level, size_t n_nodes,
+                              cudaStream_t st) {
+    if (n_nodes == 0) return cudaSuccess;
+    k_compress<<<grid_for(n_nodes, HASH_THREADS), HASH_THREADS, 0, st>>>(digests, cap, nullptr, 1, lg_sub, level,
+                                                                        n_nodes);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_two_to_one(const uint64_t* l, const uint64_t* r, size_t n, uint64_t* out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_compress<<<grid_for(n, HASH_THREADS), HASH_THREADS, 0, st>>>(const_cast<uint64_t*>(l), const_cast<uint64_t*>(r),
+                                                                  out, 0, 0, 0, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prove(const uint64_t* digests, unsigned lg_sub, size_t leaf_index, uint64_t* siblings,
+                         cudaStream_t st) {
+    if (lg_sub == 0) return cudaSuccess;
+    k_prove<<<1, 64, 0, st>>>(digests, lg_sub, leaf_index, siblings);
+    return cudaGetLastError();
+}
+
+}  // namespace pcs

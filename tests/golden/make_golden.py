@@ -371,7 +371,7 @@ def write_headers(params, C):
         f.write("\n".join(h) + "\n")
 
     # --- CUDA header ---
-    q = "__device__ __constant__"
+    q = "static __device__ __constant__"
     h = [banner, "#pragma once", "#include <stdint.h>", ""]
     h.append("namespace pcs { namespace pconst {")
     h.append(c_array("RC", params["all_round_constants"], qual=q))

@@ -1,0 +1,111 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol include/pcs.h declares,
+the host-side logic mirrors the reference, and the product never touches the oracle."""
+import ast
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from plonky2_demo_b200 import build
+
+    return build.build()
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "pcs.h")) as f:
+        h = f.read()
+    return sorted(set(re.findall(r"PCS_API[^;(]*?\b(pcs_[a-z0-9_]+)\s*\(", h)))
+
+
+def test_header_symbols_exported(built_lib):
+    syms = _declared_symbols()
+    assert len(syms) >= 25
+    L = ctypes.CDLL(built_lib)
+    for s in syms:
+        assert hasattr(L, s), f"libpcs.so does not export {s}"
+    out = subprocess.run(["nm", "-D", "--defined-only", built_lib], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (pcs_[a-z0-9_]+)", out))
+    assert exported == set(syms), exported ^ set(syms)
+
+
+def test_python_binding_matches_header(built_lib):
+    import plonky2_demo_b200 as p
+
+    assert sorted(p.SIGNATURES) == _declared_symbols()
+    assert isinstance(p.lib(), ctypes.CDLL)
+
+
+def test_no_cpu_fallback_without_device(built_lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import plonky2_demo_b200 as p
+
+    with pytest.raises(p.PcsError, match="no CPU fallback"):
+        p.init(0)
+    with pytest.raises(p.PcsError):
+        p.PoseidonHash.hash_or_noop_batch(np.zeros((2, 8), dtype=np.uint64))
+    with pytest.raises(p.PcsError):
+        p.PolynomialBatch.from_coeffs(np.zeros((2, 8), dtype=np.uint64), 3, False, 0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "plonky2_demo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            path = os.path.join(dirpath, f)
+            if f.endswith(".py"):
+                tree = ast.parse(open(path).read())
+                for node in ast.walk(tree):
+                    names = []
+                    if isinstance(node, ast.Import):
+                        names = [a.name for a in node.names]
+                    elif isinstance(node, ast.ImportFrom):
+                        names = [node.module or ""]
+                    assert not any(n.split(".")[0] == "oracle" for n in names), path
+            elif f.endswith((".cu", ".cuh", ".h")):
+                src = open(path).read()
+                assert "oracle/" not in src and "liboracle" not in src, path
+    out = subprocess.run(["ldd", os.path.join(pkg, "libpcs.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+def test_fri_params_standard_recursion_config():
+    import plonky2_demo_b200 as p
+
+    cfg = p.CircuitConfig.standard_recursion_config()
+    assert (cfg.num_wires, cfg.num_routed_wires, cfg.fri_config.rate_bits, cfg.fri_config.cap_height) == (135, 80, 3, 4)
+    assert (cfg.fri_config.proof_of_work_bits, cfg.fri_config.num_query_rounds) == (16, 28)
+    # reduction_strategies.rs:39-50 ConstantArityBits(4, 5)
+    assert cfg.fri_config.fri_params(15, False).reduction_arity_bits == [4, 4, 4]
+    assert cfg.fri_config.fri_params(20, False).reduction_arity_bits == [4, 4, 4, 4]
+    assert cfg.fri_config.fri_params(3, False).reduction_arity_bits == []
+    fp = cfg.fri_config.fri_params(15, False)
+    assert fp.lde_bits() == 18 and fp.lde_size() == 1 << 18 and fp.final_poly_bits() == 3 and fp.total_arities() == 12
+    assert cfg.fri_config.num_cap_elements() == 16
+    assert p.PoseidonGoldilocksConfig.Hasher is p.PoseidonHash and p.PoseidonGoldilocksConfig.D == 2
+    assert p.FriReductionStrategy.Fixed([3, 2, 1]).reduction_arity_bits(10, 3, 4, 28) == [3, 2, 1]
+
+
+def test_host_helpers(golden):
+    import plonky2_demo_b200 as p
+
+    assert p.reverse_index_bits(np.arange(256, dtype=np.uint64)).tolist() == golden["kats"]["reverse_index_bits_256"]
+    assert p.reverse_bits(0b01011, 5) == 0b11010  # plonky2/src/util/mod.rs:50
+    assert p.log2_strict(1 << 20) == 20
+    with pytest.raises(ValueError, match="Not a power of two: 12"):
+        p.log2_strict(12)
+    c = p.PolynomialCoeffs(np.arange(4, dtype=np.uint64))
+    assert c.lde(2).coeffs.tolist() == [0, 1, 2, 3] + [0] * 12
+    with pytest.raises(ValueError):
+        c.padded(2)
+    assert p.GOLDILOCKS_ORDER == golden["kats"]["field"]["order"]
