@@ -1,0 +1,363 @@
+#!/usr/bin/env python3
+"""Headline benchmark: LDE + Merkle commit throughput (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one PolynomialBatch::from_coeffs commit (plonky2/src/fri/oracle.rs:68-98) of
+135 polynomials of degree 2^20 at rate_bits 3, cap_height 4 (BASELINE.json configs[3]):
+batched Goldilocks coset LDE -> Poseidon leaf hashing -> Merkle levels up to the cap.
+`elems` = LDE output field elements committed = W * N = 135 * 2^23 per commit.
+
+  value : device-resident throughput (coefficients already in HBM), CUDA events on the engine's stream
+  e2e   : the same commit through the C ABI with HOST buffers: pinned host coefficients -> H2D ->
+          commit -> D2H of the Merkle cap, every step, inside the timed region
+  roofline     : dominant kernel (Poseidon leaf hashing) against the measured HBM peak
+  cpu_baseline : the CPU oracle (C/OpenMP port of the reference algorithm) on a bounded sample
+
+N > 1 (torchrun, one rank per GPU): each rank commits its own batch (independent commitments,
+no data-path collective) -> weak scaling; value = all ranks' elems / max-over-ranks time.
+
+--impl reference times the CPU port of the reference (oracle/) with all host threads on a bounded
+sample of the same workload; rank 0 only.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "lde_merkle_commit_elems_per_s"
+UNIT = "elems/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=135)
+    ap.add_argument("--lg-d", type=int, default=20)
+    ap.add_argument("--rate-bits", type=int, default=3)
+    ap.add_argument("--cap-height", type=int, default=4)
+    ap.add_argument("--cpu-sample-lg-d", type=int, default=16, help="degree_log of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"PolynomialBatch::from_coeffs commit: {a.width} polys x 2^{a.lg_d}, rate_bits {a.rate_bits}, Poseidon MerkleTree cap_height {a.cap_height}"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the reference's CPU path) on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_commit_once(width, lg_d, rate_bits, cap_height):
+    import oracle
+    from helpers import seeded_polys
+
+    coeffs = seeded_polys(width, 1 << lg_d)
+    t0 = time.perf_counter()
+    out = oracle.commit_from_coeffs(coeffs, rate_bits, cap_height)
+    dt = time.perf_counter() - t0
+    return dt, out["cap"]
+
+
+def cpu_baseline(a):
+    import oracle
+
+    lg = min(a.cpu_sample_lg_d, a.lg_d)
+    dt, _ = cpu_commit_once(a.width, lg, a.rate_bits, a.cap_height)
+    elems = a.width * (1 << (lg + a.rate_bits))
+    return {
+        "value": elems / dt,
+        "unit": UNIT,
+        "cores": oracle.num_threads(),
+        "kind": "port",
+        "sample": f"one from_coeffs commit of {a.width} x 2^{lg} (rate_bits {a.rate_bits}, cap_height {a.cap_height}), "
+                  f"{dt:.2f} s wall on {oracle.num_threads()} OpenMP threads; C port of the reference CPU algorithm (oracle/oracle.c)",
+    }
+
+
+def run_reference(a):
+    """--impl reference: CPU port of the reference path, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+
+    lg = min(a.cpu_sample_lg_d, a.lg_d)
+    for _ in range(a.warmup):
+        cpu_commit_once(a.width, lg, a.rate_bits, a.cap_height)
+    times = []
+    for _ in range(a.steps):
+        dt, _ = cpu_commit_once(a.width, lg, a.rate_bits, a.cap_height)
+        times.append(dt)
+    total = sum(times)
+    elems = a.width * (1 << (lg + a.rate_bits))
+    value = elems * a.steps / total
+    sample = (f"each step = one from_coeffs commit of {a.width} x 2^{lg} (rate_bits {a.rate_bits}, cap_height {a.cap_height}); "
+              f"bounded sample of the 2^{a.lg_d} workload; elems/s is size-normalised")
+    print(json.dumps({
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 (Goldilocks field, integer)", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.samples:
+            if ts < t0 or ts > t1 + 0.1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except Exception:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import plonky2_demo_b200 as pcs
+    from helpers import seeded_polys
+    from plonky2_demo_b200 import _ffi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream()
+    pcs.init(local_rank, stream.cuda_stream)  # engine enqueues on torch's current stream: events see its kernels
+    L = _ffi.lib()
+
+    w, lg_d, r, cap_h = a.width, a.lg_d, a.rate_bits, a.cap_height
+    d, n = 1 << lg_d, 1 << (lg_d + r)
+    elems = w * n
+
+    # synthetic input: splitmix64(0x5EED0000 + j) stream per polynomial; every rank its own batch
+    host = torch.empty((w, d), dtype=torch.int64, pin_memory=True)
+    host_np = host.numpy().view(np.uint64)
+    host_np[:] = seeded_polys(w, d, base_seed=0x5EED0000 + 1000 * rank)
+    dev_coeffs = host.to(dev, non_blocking=False)
+    cap_host = np.empty((1 << cap_h, 4), dtype=np.uint64)
+    dev_ptrs = _ffi.dev_ptr_array(dev_coeffs.data_ptr(), w, d)
+    host_ptrs = _ffi.ptr_array([host_np[j] for j in range(w)])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def commit_device():
+        h = C.c_void_p()
+        _ffi.check(L.pcs_commit_from_coeffs(dev_ptrs, w, lg_d, r, cap_h, None, 0, _ffi.PCS_DEVICE_PTRS, None, C.byref(h)))
+        return h
+
+    def commit_host():
+        h = C.c_void_p()
+        _ffi.check(L.pcs_commit_from_coeffs(host_ptrs, w, lg_d, r, cap_h, None, 0, 0, _ffi.ptr(cap_host), C.byref(h)))
+        return h
+
+    # ---- warm-up (also builds twiddle tables, fills the memory pool) ----
+    for _ in range(max(a.warmup, 3)):
+        L.pcs_batch_free(commit_device())
+    barrier()
+
+    # ---- timed: K device-resident commits ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    _ffi.check(L.pcs_timing_totals(None, None, 1))  # reset the engine's per-phase event totals
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    e0.record(stream)
+    prev = None
+    for _ in range(a.steps):
+        h = commit_device()          # asynchronous: enqueues LDE passes, leaf hashing, node levels
+        if prev is not None:
+            L.pcs_batch_free(prev)   # stream-ordered free: the next commit reuses this HBM
+        prev = h
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms_total = e0.elapsed_time(e1)
+    cap_dev = np.empty((1 << cap_h, 4), dtype=np.uint64)
+    _ffi.check(L.pcs_batch_cap(prev, _ffi.ptr(cap_dev)))
+    L.pcs_batch_free(prev)
+    ms5 = (C.c_float * 5)()
+    ncommit = C.c_uint()
+    _ffi.check(L.pcs_timing_totals(ms5, C.byref(ncommit), 1))
+    assert ncommit.value == a.steps, (ncommit.value, a.steps)
+    phase = np.array(list(ms5)) / a.steps
+    clocks = sampler.stop(t_wall0, t_wall1)
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / a.steps
+    value = world * elems * a.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
+    e2e = None
+    if not a.no_e2e:
+        for _ in range(2):
+            L.pcs_batch_free(commit_host())
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        tw0 = time.perf_counter()
+        for _ in range(a.steps):
+            h = commit_host()   # synchronous: returns once the cap is on the host
+            L.pcs_batch_free(h)
+        f1.record(stream)
+        barrier()
+        tw1 = time.perf_counter()
+        e2e_ms = max(f0.elapsed_time(f1), 1e3 * (tw1 - tw0))
+        te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms = float(te.item())
+        assert np.array_equal(cap_host, cap_dev), "host-path and device-path caps differ"
+        e2e = {"value": world * elems * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": w * d * 8, "d2h_bytes_per_step": (1 << cap_h) * 32,
+               "ms_per_step": e2e_ms / a.steps,
+               "note": "pinned host coefficients -> pcs_commit_from_coeffs (host pointers) -> Merkle cap on host; "
+                       "LDE rows and digests stay device-resident behind the batch handle"}
+
+    # ---- roofline of the dominant kernel (leaf hashing) + per-phase table ----
+    peaks, peak_src = measured_peaks()
+    peak = float(peaks["hbm_gbs"])
+    wt = w
+    leaf_bytes = wt * n * 8 + n * 32                       # read every LDE element once, write one digest per leaf
+    lde_bytes = w * d * 8 + w * n * 8                       # read coefficients, write LDE
+    node_bytes = 3 * 32 * (n - (1 << cap_h))                # each node: read 2 children, write 1 digest
+    commit_bytes = lde_bytes + 2 * (n - (1 << cap_h)) * 32 + (1 << cap_h) * 32
+    leaf_ms, lde_ms, node_ms = phase[3], phase[1], phase[4]
+    n_perm_leaf = n * ((wt + 7) // 8) if wt > 4 else 0
+    n_perm_node = n - (1 << cap_h)
+    roofline = {"bound": "hbm", "kernel": "k_hash_cols (Poseidon leaf hashing, 17 permutations per 135-element leaf)",
+                "achieved": leaf_bytes / (leaf_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": leaf_bytes / (leaf_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": leaf_bytes, "launch_ms": leaf_ms,
+                "note": "integer-pipe bound, not HBM bound: see int_pipe"}
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    int_pipe = {"permutations_per_s": (n_perm_leaf) / (leaf_ms * 1e-3),
+                "clk_per_permutation_per_sm_lane": (leaf_ms * 1e-3) * sm_mhz * 1e6 * 148 / max(n_perm_leaf, 1),
+                "sm_mhz_used": sm_mhz}
+    kernels = {
+        "lde": {"ms": lde_ms, "algorithmic_bytes": lde_bytes, "GBps": lde_bytes / (lde_ms * 1e-3) / 1e9, "frac_hbm": lde_bytes / (lde_ms * 1e-3) / 1e9 / peak},
+        "leaf_hash": {"ms": leaf_ms, "algorithmic_bytes": leaf_bytes, "GBps": roofline["achieved"], "frac_hbm": roofline["frac"], "permutations": n_perm_leaf},
+        "node_levels": {"ms": node_ms, "algorithmic_bytes": node_bytes, "GBps": node_bytes / (node_ms * 1e-3) / 1e9, "permutations": n_perm_node},
+        "commit": {"ms": ms_per_step, "algorithmic_bytes": commit_bytes, "GBps": commit_bytes / (ms_per_step * 1e-3) / 1e9,
+                   "frac_hbm": commit_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
+    }
+
+    lg_passes = (lg_d + 9) // 10 if lg_d else 1
+    launches_per_step = lg_passes + 1 + (lg_d + r - cap_h)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 (Goldilocks field, integer)", "data": "synthetic",
+        "config": {"workload": workload_name(a), "elems_per_step_per_gpu": elems, "input_coeff_elems_per_s": value / (1 << r),
+                   "l2_policy": "inputs larger than L2 (1.13 GB coefficients, 9.06 GB LDE per step)",
+                   "parallelism": f"{world} independent commitments, one per GPU" if world > 1 else "single GPU"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
+        "roofline": roofline, "int_pipe": int_pipe, "kernels": kernels,
+        "phase_ms": {"IFFT": phase[0], "FFT + blinding": phase[1], "transpose LDEs": phase[2], "leaf hashing": phase[3], "node levels": phase[4]},
+    }
+    if rank == 0:
+        if not a.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(a)
+            # parity spot-check of the benchmark itself: same seeds at the CPU sample size
+            lg = min(a.cpu_sample_lg_d, a.lg_d)
+            from helpers import seeded_polys as sp
+            import oracle
+            small = sp(w, 1 << lg, base_seed=0x5EED0000)
+            b = pcs.PolynomialBatch.from_coeffs(small, r, False, cap_h)
+            ok = bool(np.array_equal(b.merkle_tree.cap.hashes, oracle.commit_from_coeffs(small, r, cap_h)["cap"]))
+            out["parity_check"] = {"cap_equal_to_oracle_at_sample_size": ok, "lg_d": lg}
+            b.free()
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

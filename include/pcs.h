@@ -136,6 +136,10 @@ PCS_API const uint64_t* pcs_batch_cap_dev(const pcs_batch* b);
  * Synchronises the stream.                                                                         */
 PCS_API int pcs_batch_timings(const pcs_batch* b, float ms[5]);
 PCS_API void pcs_batch_free(pcs_batch* b);
+/* Phase times (same five slots as pcs_batch_timings) summed over every batch freed since the last
+ * reset, and how many batches that was; lets a caller free each batch immediately (so the next
+ * commit reuses its HBM) and still read per-kernel times afterwards.  Synchronises the stream. */
+PCS_API int pcs_timing_totals(float ms[5], unsigned* n_commits, int reset);
 
 #ifdef __cplusplus
 }

@@ -28,24 +28,33 @@ static inline gl_t gl_canon(gl_t x) { return x >= GL_P ? x - GL_P : x; }
 
 static inline gl_t gl_add(gl_t a, gl_t b) {
     uint64_t s = a + b;
-    uint64_t over = s < a;
-    uint64_t s2 = s + over * GL_EPS;
-    if (s2 < s) s2 += GL_EPS; /* double overflow: only if both inputs > p */
+    uint64_t over = (uint64_t)0 - (uint64_t)(s < a); /* all-ones on wrap */
+    uint64_t s2 = s + (over & GL_EPS);
+    if (__builtin_expect(s2 < s, 0)) s2 += GL_EPS; /* double overflow: only if both inputs > p (rare) */
     return s2;
 }
 
 static inline gl_t gl_sub(gl_t a, gl_t b) {
     uint64_t d = a - b;
-    uint64_t under = a < b;
-    uint64_t d2 = d - under * GL_EPS;
-    if (d2 > d) d2 -= GL_EPS; /* double underflow */
+    uint64_t under = (uint64_t)0 - (uint64_t)(a < b);
+    uint64_t d2 = d - (under & GL_EPS);
+    if (__builtin_expect(d2 > d, 0)) d2 -= GL_EPS; /* double underflow (rare) */
     return d2;
 }
 
 /* x + y mod 2^64 with the wrap folded back in; exact when x + y < 2^64 + p. */
+/* Branch-free like the reference's x86 `add; sbb` trick (goldilocks_field.rs:309-334): the wrap
+ * happens ~50% of the time on random data, so a branch here would be mispredicted every other call. */
 static inline uint64_t gl_add_no_canon(uint64_t x, uint64_t y) {
-    uint64_t r = x + y;
-    return r + (r < x ? GL_EPS : 0);
+    uint64_t r, adj;
+#if defined(__x86_64__)
+    __asm__("add %2, %0\n\tsbb %k1, %k1" : "=&r"(r), "=&r"(adj) : "r"(y), "0"(x) : "cc");
+#else
+    r = x + y;
+    adj = (uint64_t)0 - (uint64_t)(r < x);
+    adj &= GL_EPS;
+#endif
+    return r + adj;
 }
 
 static inline gl_t gl_reduce96(uint64_t lo, uint32_t hi) {
@@ -56,7 +65,7 @@ static inline gl_t gl_reduce128(u128 x) {
     uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
     uint64_t hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
     uint64_t t0 = lo - hi_hi;
-    if (lo < hi_hi) t0 -= GL_EPS;
+    if (__builtin_expect(lo < hi_hi, 0)) t0 -= GL_EPS; /* "exceedingly rare" (goldilocks_field.rs:362) */
     uint64_t t1 = hi_lo * GL_EPS;
     return gl_add_no_canon(t0, t1);
 }

@@ -217,17 +217,19 @@ static inline void constant_layer(gl_t* s, int round) {
  * (poseidon_goldilocks.rs:217-248) splits every lane in 32-bit halves so that all sums fit in
  * u64; we use the same split with the plain circulant sums (result identical). */
 static inline void mds_layer(gl_t* s) {
-    uint64_t lo[PW], hi[PW], out[PW];
+    /* doubled halves so that the circulant index (i + r) needs no modulo */
+    uint64_t lo[2 * PW], hi[2 * PW], out[PW];
     for (int i = 0; i < PW; i++) {
-        lo[i] = (uint32_t)s[i];
-        hi[i] = s[i] >> 32;
+        lo[i] = lo[i + PW] = (uint32_t)s[i];
+        hi[i] = hi[i + PW] = s[i] >> 32;
     }
+#pragma GCC unroll 12
     for (int r = 0; r < PW; r++) {
         uint64_t al = 0, ah = 0;
+#pragma GCC unroll 12
         for (int i = 0; i < PW; i++) {
-            int k = (i + r) % PW;
-            al += lo[k] * MDS_MATRIX_CIRC[i];
-            ah += hi[k] * MDS_MATRIX_CIRC[i];
+            al += lo[i + r] * MDS_MATRIX_CIRC[i];
+            ah += hi[i + r] * MDS_MATRIX_CIRC[i];
         }
         al += lo[r] * MDS_MATRIX_DIAG[r];
         ah += hi[r] * MDS_MATRIX_DIAG[r];

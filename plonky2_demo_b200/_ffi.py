@@ -42,6 +42,7 @@ SIGNATURES = {
     "pcs_batch_cap_dev": (C.c_void_p, [C.c_void_p]),
     "pcs_batch_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "pcs_batch_free": (None, [C.c_void_p]),
+    "pcs_timing_totals": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_uint), C.c_int]),
 }
 
 _lib = None

@@ -11,13 +11,34 @@ namespace pcs {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 
+struct PendingEvents { cudaEvent_t ev[6]; };
+
 struct Ctx {
+    std::vector<PendingEvents> pending;   // events of freed batches, not yet folded into totals
+    float totals[5] = {0, 0, 0, 0, 0};
+    unsigned n_totals = 0;
     bool init = false;
     int device = -1;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
 };
 static Ctx g_ctx;
+
+// fold completed/pending event sets into the running totals (caller has synchronised the stream)
+static void drain_pending() {
+    for (auto& pe : g_ctx.pending) {
+        bool ok = true;
+        float ms[5];
+        for (int i = 0; i < 5 && ok; i++) ok = cudaEventElapsedTime(&ms[i], pe.ev[i], pe.ev[i + 1]) == cudaSuccess;
+        if (ok) {
+            for (int i = 0; i < 5; i++) g_ctx.totals[i] += ms[i];
+            g_ctx.n_totals++;
+        }
+        for (auto& e : pe.ev) cudaEventDestroy(e);
+    }
+    g_ctx.pending.clear();
+    cudaGetLastError();
+}
 
 static int fail(int code, const std::string& msg) {
     set_error(msg);
@@ -63,6 +84,7 @@ struct pcs_batch {
     uint64_t* cap = nullptr;      // [2^cap][4]
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool has_ifft = false;
+    bool committed = false;  // all six events recorded
 };
 
 extern "C" {
@@ -110,6 +132,7 @@ int pcs_init(int device, void* stream) {
 void pcs_shutdown(void) {
     if (!g_ctx.init) return;
     cudaStreamSynchronize(g_ctx.stream);
+    drain_pending();
     ntt_plans_free();
     if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.stream);
     g_ctx = Ctx();
@@ -282,8 +305,18 @@ void pcs_batch_free(pcs_batch* b) {
     if (b->lde) cudaFreeAsync(b->lde, st);
     if (b->digests) cudaFreeAsync(b->digests, st);
     if (b->cap) cudaFreeAsync(b->cap, st);
-    for (auto& e : b->ev)
-        if (e) cudaEventDestroy(e);
+    if (b->ev[5] && b->committed) {
+        PendingEvents pe;
+        for (int i = 0; i < 6; i++) pe.ev[i] = b->ev[i];
+        g_ctx.pending.push_back(pe);
+        if (g_ctx.pending.size() > 256) {
+            cudaStreamSynchronize(st);
+            drain_pending();
+        }
+    } else {
+        for (auto& e : b->ev)
+            if (e) cudaEventDestroy(e);
+    }
     delete b;
 }
 
@@ -383,6 +416,7 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
         PCS_CUDA(cudaStreamSynchronize(st));  // host inputs must not be reused before the copies finish
     }
     guard.armed = false;
+    b->committed = true;
     *out = b;
     return PCS_OK;
 }
@@ -496,6 +530,20 @@ int pcs_batch_timings(const pcs_batch* b, float ms[5]) {
     if (!b || !ms) return fail(PCS_ERR_ARG, "NULL pointer");
     PCS_CUDA(cudaStreamSynchronize(g_ctx.stream));
     for (int i = 0; i < 5; i++) PCS_CUDA(cudaEventElapsedTime(&ms[i], b->ev[i], b->ev[i + 1]));
+    return PCS_OK;
+}
+
+int pcs_timing_totals(float ms[5], unsigned* n_commits, int reset) {
+    PCS_NEED_INIT();
+    PCS_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    drain_pending();
+    if (ms)
+        for (int i = 0; i < 5; i++) ms[i] = g_ctx.totals[i];
+    if (n_commits) *n_commits = g_ctx.n_totals;
+    if (reset) {
+        for (auto& t : g_ctx.totals) t = 0;
+        g_ctx.n_totals = 0;
+    }
     return PCS_OK;
 }
 
