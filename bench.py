@@ -193,11 +193,16 @@ def run_ours(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    stream = torch.cuda.current_stream()
-    pcs.init(local_rank, stream.cuda_stream)  # engine enqueues on torch's current stream: events see its kernels
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    # A dedicated (non-default) stream shared by torch and the engine: the engine enqueues every kernel on
+    # it, so torch.cuda.Event records on the same stream bracket exactly the engine's work.
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    pcs.init(local_rank, stream.cuda_stream)
+    assert pcs.stream() == stream.cuda_stream
     L = _ffi.lib()
 
     w, lg_d, r, cap_h = a.width, a.lg_d, a.rate_bits, a.cap_height
@@ -244,10 +249,9 @@ def run_ours(a):
     e0.record(stream)
     prev = None
     for _ in range(a.steps):
-        h = commit_device()          # asynchronous: enqueues LDE passes, leaf hashing, node levels
         if prev is not None:
             L.pcs_batch_free(prev)   # stream-ordered free: the next commit reuses this HBM
-        prev = h
+        prev = commit_device()       # asynchronous: enqueues LDE passes, leaf hashing, node levels
     e1.record(stream)
     barrier()
     t_wall1 = time.perf_counter()

@@ -7,14 +7,22 @@
 // reference's own `consistency` test (poseidon.rs:777-790) licenses any algebraically equal
 // evaluation order, and tests/ pin this kernel to the reference KATs (poseidon_goldilocks.rs:461-482).
 //
-// Design for the B200 integer pipes (no tensor cores: 64-bit modular arithmetic):
-//  * full-round MDS: every lane is split in 32-bit halves; each output row is two chains of
-//    IMAD.WIDE.U32 (32x6-bit MAC into a 64-bit accumulator, < 2^42), one 96-bit fold per row.
-//    The NEXT round's constant is pre-loaded into the accumulator, so constant_layer is free.
-//  * partial rounds: "lazy" form (tests/golden/make_golden.py:derive_lazy_tables).  Lanes 1..11
-//    are never materialised during the 22 rounds; each round's lane-0 value is a dot product of
-//    compile-time constants with the 11 post-init lanes and the earlier S-box outputs,
-//    accumulated unreduced (one reduction per round instead of twelve).
+// Design for the B200 integer pipes (no tensor cores: 64-bit modular arithmetic).  Measured rates
+// (profiles/r01_intpipe.md): IADD3 128/clk/SM, IMAD/LOP3/SHF 64, IMAD.WIDE 32 -- so the wide
+// multiplier is the scarce unit and is reserved for the S-boxes (4 IMAD.WIDE per modmul):
+//  * MDS layer = add/shift network, zero multiplies.  Each lane is split in 32-bit halves; the
+//    12-point circulant product of a half is computed exactly in int64 through the factorisation
+//    x^12 - 1 = prod over zeta in {1,-1,i,-i} of (x^3 - zeta) with x^4 = zeta (three 4-point integer
+//    DFTs, three 3x3 twisted products whose constants are (2+i), (-4-i), (16-i), [16,32,16],
+//    [-1,-8,2] -- the MDS matrix was designed to have these -- and three inverse DFTs).  Same
+//    mathematics as the reference's x86 path (poseidon_goldilocks.rs:217-248,307-441), derived
+//    and verified independently in tests/golden/make_golden.py:mds_network_check.
+//    The next round's constant is folded into the network's additions (3-input IADD3), so
+//    constant_layer costs nothing; one 96-bit fold per lane brings the result back to 64 bits.
+//  * partial rounds use the dense network too, with the constants pushed through the linear layer
+//    so that only lane 0 receives one (FAST_PARTIAL_FIRST_ROUND_CONSTANT once, then the scalar
+//    FAST_PARTIAL_ROUND_CONSTANTS[r]); the sparse "fast" matrices of poseidon.rs:584-596 would
+//    need 23 full 64x64 multiplies per round on the scarce pipe.
 #pragma once
 #include "gl64.cuh"
 #include "poseidon_constants.cuh"
@@ -31,117 +39,105 @@ __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
     return gl::mul(x3, x4);
 }
 
-// value = lo + hi*2^64 (hi < 2^32) -> canonical
-__device__ __forceinline__ uint64_t reduce96(uint64_t lo, uint32_t hi) {
-    uint64_t t1 = ((uint64_t)hi << 32) - hi;  // hi * EPS
-    uint64_t r = lo + t1;
-    if (r < t1) r += gl::EPS;
-    return gl::canon(r);
+// y = circ-correlation(s) + 8*s0*e0 + add, for 12 non-negative 32-bit inputs; exact in int64
+// (|intermediates| < 2^40, results < 2^43 + add).
+__device__ __forceinline__ void mds_half(const uint32_t (&s)[12], const uint32_t (&add)[12], uint64_t (&y)[12]) {
+    int64_t A[3], B[3], P[3], Q[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        int64_t s0 = s[j], s3 = s[j + 3], s6 = s[j + 6], s9 = s[j + 9];
+        int64_t u = s0 + s6, v = s3 + s9;
+        A[j] = u + v;    // S_j(1)
+        B[j] = u - v;    // S_j(-1)
+        P[j] = s0 - s6;  // Re S_j(i)
+        Q[j] = s3 - s9;  // Im S_j(i)
+    }
+    // zeta = 1: cyclic 3-product with [16, 32, 16]
+    int64_t t = A[0] + A[1] + A[2];
+    int64_t Ya[3] = {(t + A[2]) << 4, (t + A[0]) << 4, (t + A[1]) << 4};
+    // zeta = -1: negacyclic 3-product with [-1, -8, 2]
+    int64_t Yb[3] = {(B[2] << 3) - (B[1] << 1) - B[0],
+                     -(B[0] << 3) - B[1] - (B[2] << 1),
+                     (B[0] << 1) - (B[1] << 3) - B[2]};
+    // zeta = i: i-twisted 3-product with (2+i), (-4-i), (16-i)
+    int64_t re[3], im[3];
+    re[0] = (P[0] << 1) - Q[0] + P[1] - (Q[1] << 4) + P[2] + (Q[2] << 2);
+    im[0] = P[0] + (Q[0] << 1) + (P[1] << 4) + Q[1] - (P[2] << 2) + Q[2];
+    re[1] = -(P[0] << 2) + Q[0] + (P[1] << 1) - Q[1] + P[2] - (Q[2] << 4);
+    im[1] = -P[0] - (Q[0] << 2) + P[1] + (Q[1] << 1) + (P[2] << 4) + Q[2];
+    re[2] = (P[0] << 4) + Q[0] - (P[1] << 2) + Q[1] + (P[2] << 1) - Q[2];
+    im[2] = -P[0] + (Q[0] << 4) - P[1] - (Q[1] << 2) + P[2] + (Q[2] << 1);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        int64_t e1 = Ya[j] + Yb[j], e2 = Ya[j] - Yb[j];
+        y[j] = (uint64_t)(e1 + re[j] + (int64_t)add[j]);
+        y[j + 3] = (uint64_t)(e2 + im[j] + (int64_t)add[j + 3]);
+        y[j + 6] = (uint64_t)(e1 - re[j] + (int64_t)add[j + 6]);
+        y[j + 9] = (uint64_t)(e2 - im[j] + (int64_t)add[j + 9]);
+    }
+    y[0] += (uint64_t)s[0] << 3;  // MDS_MATRIX_DIAG[0] = 8
 }
 
-// s <- MDS * s  (+ optional constant vector, added for free inside the accumulators)
-template <bool ADD_RC>
-__device__ __forceinline__ void mds_full(uint64_t (&s)[12], const uint64_t* __restrict__ rc) {
-    constexpr uint32_t CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    uint32_t lo[12], hi[12];
+// s <- MDS * s + rc   (rc = nullptr: no constant; lane0_only: rc[0] is added to lane 0 only)
+template <int RC_MODE /*0 none, 1 all 12 lanes, 2 lane 0 only*/>
+__device__ __forceinline__ void mds_layer(uint64_t (&s)[12], const uint64_t* __restrict__ rc) {
+    uint32_t lo[12], hi[12], alo[12], ahi[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) {
         lo[i] = (uint32_t)s[i];
         hi[i] = (uint32_t)(s[i] >> 32);
+        uint64_t c = (RC_MODE == 1 || (RC_MODE == 2 && i == 0)) ? rc[i] : 0;
+        alo[i] = (uint32_t)c;
+        ahi[i] = (uint32_t)(c >> 32);
     }
+    uint64_t L[12], H[12];
+    mds_half(lo, alo, L);
+    mds_half(hi, ahi, H);
 #pragma unroll
     for (int r = 0; r < 12; r++) {
-        uint64_t al, ah;
-        if (ADD_RC) {
-            uint64_t c = rc[r];
-            al = (uint32_t)c;
-            ah = c >> 32;
-        } else {
-            al = 0;
-            ah = 0;
-        }
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            al += (uint64_t)lo[(i + r) % 12] * CIRC[i];
-            ah += (uint64_t)hi[(i + r) % 12] * CIRC[i];
-        }
-        if (r == 0) {
-            al += (uint64_t)lo[0] * 8u;
-            ah += (uint64_t)hi[0] * 8u;
-        }
-        // value = al + ah*2^32, al, ah < 2^43
-        uint64_t hs = ah << 32;
-        uint64_t l = al + hs;
-        uint32_t h = (uint32_t)(ah >> 32) + (l < hs);
-        s[r] = reduce96(l, h);
+        // value = L + H * 2^32, L, H < 2^44
+        uint64_t hs = H[r] << 32;
+        uint64_t l = L[r] + hs;
+        uint32_t top = (uint32_t)(H[r] >> 32) + (l < hs);
+        s[r] = gl::reduce96(l, top);
     }
 }
 
-// The permutation.  Input lanes must be canonical; output lanes are canonical.
+// The permutation.  Input lanes: any u64 (loose); output lanes: canonical.
 __device__ __forceinline__ void poseidon12(uint64_t (&s)[12]) {
     using namespace pconst;
-    // ---- first 4 full rounds; RC of round 0 added explicitly, the rest fused into the MDS ----
+    // ---- first 4 full rounds; RC of round 0 added explicitly, later ones inside the MDS network ----
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl::add(s[i], RC[i]);
+    for (int i = 0; i < 12; i++) s[i] = gl::add_lc(s[i], RC[i]);
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
 #pragma unroll
         for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
-        // after round 3 the next additive constant is FIRST_RC (partial_first_constant_layer)
-        mds_full<true>(s, r < 3 ? &RC[12 * (r + 1)] : FIRST_RC);
+        // after round 3 the additive constant is FAST_PARTIAL_FIRST_ROUND_CONSTANT (poseidon.rs:312)
+        mds_layer<1>(s, r < 3 ? &RC[12 * (r + 1)] : FIRST_RC);
     }
-
-    // ---- mds_partial_layer_init (poseidon.rs:340-366): t_c = sum_r s_r * INIT[r][c], c,r in 1..11
-    uint64_t t[12];
-    t[0] = s[0];
-#pragma unroll
-    for (int c = 1; c < 12; c++) {
-        gl::Acc192 acc;
-        gl::acc_init(acc);
-#pragma unroll
-        for (int r = 1; r < 12; r++) gl::acc_mac(acc, s[r], INIT_T[(c - 1) * 11 + (r - 1)]);
-        t[c] = gl::acc_reduce(acc);
+    // ---- 22 partial rounds: s0 <- sbox(s0) + c_r ; s <- M s   (constants pushed to lane 0) ----
+    // round r's scalar constant is added by the PREVIOUS network (after the s-box it reads
+    // PARTIAL_RC[r]); equivalently: s0 = sbox(s0); s = M*s' where s'0 = s0 + c_r.
+#pragma unroll 1
+    for (int r = 0; r < 22; r++) {
+        s[0] = gl::add_lc(sbox7(s[0]), PARTIAL_RC[r]);
+        mds_layer<0>(s, nullptr);
     }
-
-    // ---- 22 lazy partial rounds ----
-    uint64_t x[22];
-    uint64_t s0 = t[0];
-#pragma unroll
-    for (int k = 0; k < 22; k++) {
-        uint64_t xk = gl::add(sbox7(s0), PARTIAL_RC[k]);
-        x[k] = xk;
-        gl::Acc192 acc;
-        gl::acc_init(acc);
-        gl::acc_mac(acc, xk, 25);  // M00 = circ[0] + diag[0]
-#pragma unroll
-        for (int i = 1; i < 12; i++) gl::acc_mac(acc, t[i], W_HATS[k * 11 + i - 1]);
-#pragma unroll
-        for (int q = 0; q < k; q++) gl::acc_mac(acc, x[q], LAZY_C[k * (k - 1) / 2 + q]);
-        s0 = gl::acc_reduce(acc);
-    }
-    s[0] = s0;
-#pragma unroll
-    for (int i = 1; i < 12; i++) {
-        gl::Acc192 acc;
-        gl::acc_init(acc);
-        gl::acc_add64(acc, t[i]);
-#pragma unroll
-        for (int q = 0; q < 22; q++) gl::acc_mac(acc, x[q], VS[q * 11 + i - 1]);
-        s[i] = gl::acc_reduce(acc);
-    }
-
     // ---- last 4 full rounds ----
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl::add(s[i], RC[12 * 26 + i]);
+    for (int i = 0; i < 12; i++) s[i] = gl::add_lc(s[i], RC[12 * 26 + i]);
 #pragma unroll 1
     for (int r = 26; r < 30; r++) {
 #pragma unroll
         for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
         if (r < 29)
-            mds_full<true>(s, &RC[12 * (r + 1)]);
+            mds_layer<1>(s, &RC[12 * (r + 1)]);
         else
-            mds_full<false>(s, nullptr);
+            mds_layer<0>(s, nullptr);
     }
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = gl::canon(s[i]);
 }
 
 }  // namespace pcs

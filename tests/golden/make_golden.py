@@ -343,6 +343,69 @@ def poseidon_lazy(params, C, state):
     return s
 
 
+def poseidon_dense_partial(params, state):
+    """The form the GPU kernel uses (csrc/poseidon.cuh): full rounds as in the reference, partial
+    rounds with the DENSE MDS but with the round constants pushed through the linear layer
+    (first half of the fast-form derivation only): s += FIRST_RC ; 22 x { s0 = sbox(s0) + c_r ; s = M s }."""
+    rc = params["all_round_constants"]
+    M = mds_matrix(params)
+    s = [x % P for x in state]
+    r = 0
+    for _ in range(4):
+        s = [pow((s[i] + rc[12 * r + i]) % P, 7, P) for i in range(W)]
+        s = mat_vec(M, s)
+        r += 1
+    s = [(s[i] + params["fast_partial_first_round_constant"][i]) % P for i in range(W)]
+    for k in range(N_PARTIAL):
+        s[0] = (pow(s[0], 7, P) + params["fast_partial_round_constants"][k]) % P
+        s = mat_vec(M, s)
+    r += N_PARTIAL
+    for _ in range(4):
+        s = [pow((s[i] + rc[12 * r + i]) % P, 7, P) for i in range(W)]
+        s = mat_vec(M, s)
+        r += 1
+    return s
+
+
+def mds_network(circ, s):
+    """Add/shift network for y_r = sum_i circ[i] * s[(r+i) % 12] on integers (csrc/poseidon.cuh:mds_half).
+    x^12 - 1 = prod_{zeta^4=1} (x^3 - zeta): 4-point DFTs of the three stride-3 subsequences, one
+    zeta-twisted 3x3 product per frequency, inverse DFTs.  The frequency-domain constants are
+    derived here from `circ` (not copied): K = DFT4(c')(1)/4, N = DFT4(c')(-1)/4, Z = DFT4(c')(i)/2."""
+    cp = [circ[(-m) % 12] for m in range(12)]  # correlation -> convolution kernel
+    K, N, Z = [], [], []
+    for b in range(3):
+        x0, x1, x2, x3 = (cp[3 * k + b] for k in range(4))
+        assert (x0 + x1 + x2 + x3) % 4 == 0 and (x0 - x1 + x2 - x3) % 4 == 0 and (x0 - x2) % 2 == 0 and (x1 - x3) % 2 == 0
+        K.append((x0 + x1 + x2 + x3) // 4)
+        N.append((x0 - x1 + x2 - x3) // 4)
+        Z.append(complex((x0 - x2) // 2, (x1 - x3) // 2))
+    assert K == [16, 32, 16] and N == [-1, -8, 2] and Z == [2 + 1j, -4 - 1j, 16 - 1j], (K, N, Z)
+    A, B, Pq = [0] * 3, [0] * 3, [0] * 3
+    for j in range(3):
+        u, v = s[j] + s[j + 6], s[j + 3] + s[j + 9]
+        A[j], B[j], Pq[j] = u + v, u - v, complex(s[j] - s[j + 6], s[j + 3] - s[j + 9])
+    y = [0] * 12
+    for j in range(3):
+        ya = sum(A[a] * K[(j - a) % 3] for a in range(3))
+        yb = sum((1 if a + b == j else -1) * B[a] * N[b] for a in range(3) for b in range(3) if (a + b) % 3 == j)
+        yc = sum((1 if a + b == j else 1j) * Pq[a] * Z[b] for a in range(3) for b in range(3) if (a + b) % 3 == j)
+        re, im = int(yc.real), int(yc.imag)
+        y[j], y[j + 3], y[j + 6], y[j + 9] = ya + yb + re, ya - yb + im, ya + yb - re, ya - yb - im
+    return y
+
+
+def mds_network_check(params):
+    import random
+
+    rnd = random.Random(7)
+    circ = params["mds_circ"]
+    for _ in range(200):
+        s = [rnd.randrange(1 << 32) for _ in range(12)]
+        direct = [sum(circ[i] * s[(r + i) % 12] for i in range(12)) for r in range(12)]
+        assert mds_network(circ, s) == direct
+
+
 def c_array(name, vals, per_line=4, ctype="uint64_t", qual="static const"):
     out = [f"{qual} {ctype} {name}[{len(vals)}] = {{"]
     for i in range(0, len(vals), per_line):
@@ -406,6 +469,10 @@ def main():
     derived = derive_fast_tables(params)
     for k, v in derived.items():
         assert v == params[k], f"derived table {k} differs from the reference's"
+    # 2b. the forms the CUDA kernels use: dense partial rounds with pushed constants; MDS add network
+    mds_network_check(params)
+    for kv in kat["poseidon12_kats"]:
+        assert poseidon_dense_partial(params, kv["input"]) == kv["output"], "dense-partial KAT mismatch"
     # 3. lazy partial-round tables agree too
     C = derive_lazy_tables(params)
     import random
