@@ -20,14 +20,18 @@
 //    The next round's constant is folded into the network's additions (3-input IADD3), so
 //    constant_layer costs nothing; one 96-bit fold per lane brings the result back to 64 bits.
 //  * partial rounds use the dense network too, with the constants pushed through the linear layer
-//    so that only lane 0 receives one (FAST_PARTIAL_FIRST_ROUND_CONSTANT once, then the scalar
-//    FAST_PARTIAL_ROUND_CONSTANTS[r]); the sparse "fast" matrices of poseidon.rs:584-596 would
-//    need 23 full 64x64 multiplies per round on the scarce pipe.
+//    (FAST_PARTIAL_FIRST_ROUND_CONSTANT once, then the scalar FAST_PARTIAL_ROUND_CONSTANTS[r] times
+//    the first MDS column); the sparse "fast" matrices of poseidon.rs:584-596 would need 23 full
+//    64x64 multiplies per round on the scarce pipe.
 #pragma once
 #include "gl64.cuh"
 #include "poseidon_constants.cuh"
 
 namespace pcs {
+
+#ifndef PCS_SBOX_GROUP
+#define PCS_SBOX_GROUP 12
+#endif
 
 constexpr int SPONGE_WIDTH = 12;
 constexpr int SPONGE_RATE = 8;
@@ -94,47 +98,45 @@ __device__ __forceinline__ void mds_layer(uint64_t (&s)[12], const uint64_t* __r
     mds_half(lo, alo, L);
     mds_half(hi, ahi, H);
 #pragma unroll
-    for (int r = 0; r < 12; r++) {
-        // value = L + H * 2^32, L, H < 2^44
-        uint64_t hs = H[r] << 32;
-        uint64_t l = L[r] + hs;
-        uint32_t top = (uint32_t)(H[r] >> 32) + (l < hs);
-        s[r] = gl::reduce96(l, top);
-    }
+    for (int r = 0; r < 12; r++) s[r] = gl::fold_halves(L[r], H[r]);
 }
 
 // The permutation.  Input lanes: any u64 (loose); output lanes: canonical.
+//
+// ONE round loop for all 30 rounds (the body is ~22 KB of SASS and must stay resident in the SM's
+// instruction cache: with separate full/partial loop bodies the kernel was instruction-fetch bound,
+// profiles/r01_leafhash_v2.md).  Every round is  "s-box ; s = M s + ROUND_ADD[r]"  where the s-box
+// covers all lanes in the 8 full rounds and lane 0 only in the 22 partial rounds (warp-uniform
+// branch) and ROUND_ADD[r] is the constant needed by the NEXT s-box layer moved behind the linear
+// layer (tests/golden/make_golden.py:round_addends); it is absorbed by 3-input adds of the network.
 __device__ __forceinline__ void poseidon12(uint64_t (&s)[12]) {
     using namespace pconst;
-    // ---- first 4 full rounds; RC of round 0 added explicitly, later ones inside the MDS network ----
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl::add_lc(s[i], RC[i]);
 #pragma unroll 1
-    for (int r = 0; r < 4; r++) {
+    for (int r = 0; r < 30; r++) {
+        if (r < 4 || r >= 26) {
+#if PCS_SBOX_GROUP == 12
 #pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
-        // after round 3 the additive constant is FAST_PARTIAL_FIRST_ROUND_CONSTANT (poseidon.rs:312)
-        mds_layer<1>(s, r < 3 ? &RC[12 * (r + 1)] : FIRST_RC);
-    }
-    // ---- 22 partial rounds: s0 <- sbox(s0) + c_r ; s <- M s   (constants pushed to lane 0) ----
-    // round r's scalar constant is added by the PREVIOUS network (after the s-box it reads
-    // PARTIAL_RC[r]); equivalently: s0 = sbox(s0); s = M*s' where s'0 = s0 + c_r.
+            for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
+#else
+            // S-box layer as a loop over groups of lanes; the state is rotated by one group after
+            // each pass (register moves), so the loop body is 1/(12/GROUP) of the code.
 #pragma unroll 1
-    for (int r = 0; r < 22; r++) {
-        s[0] = gl::add_lc(sbox7(s[0]), PARTIAL_RC[r]);
-        mds_layer<0>(s, nullptr);
-    }
-    // ---- last 4 full rounds ----
+            for (int g = 0; g < 12 / PCS_SBOX_GROUP; g++) {
+                uint64_t t[PCS_SBOX_GROUP];
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl::add_lc(s[i], RC[12 * 26 + i]);
-#pragma unroll 1
-    for (int r = 26; r < 30; r++) {
+                for (int i = 0; i < PCS_SBOX_GROUP; i++) t[i] = sbox7(s[i]);
 #pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
-        if (r < 29)
-            mds_layer<1>(s, &RC[12 * (r + 1)]);
-        else
-            mds_layer<0>(s, nullptr);
+                for (int i = 0; i < 12 - PCS_SBOX_GROUP; i++) s[i] = s[i + PCS_SBOX_GROUP];
+#pragma unroll
+                for (int i = 0; i < PCS_SBOX_GROUP; i++) s[12 - PCS_SBOX_GROUP + i] = t[i];
+            }
+#endif
+        } else {
+            s[0] = sbox7(s[0]);
+        }
+        mds_layer<1>(s, &ROUND_ADD[12 * r]);
     }
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl::canon(s[i]);

@@ -367,6 +367,53 @@ def poseidon_dense_partial(params, state):
     return s
 
 
+def round_addends(params):
+    """Unified per-round additive constants for the GPU's single round loop (csrc/poseidon.cuh):
+        s += RC[0]; for r in 0..29: { s-box (all lanes if full round else lane 0); s = M s + ADD[r] }
+    ADD[r] is the constant the NEXT s-box layer needs, moved behind the linear layer:
+      r = 0..2   : RC[r+1]
+      r = 3      : FAST_PARTIAL_FIRST_ROUND_CONSTANT
+      r = 4..25  : PARTIAL_RC[r-4] * M[:,0]   (the scalar added to lane 0 after the s-box, pushed through M)
+                   (+ RC[26] for r = 25)
+      r = 26..28 : RC[r+1]
+      r = 29     : 0
+    """
+    rc = params["all_round_constants"]
+    M = mds_matrix(params)
+    col0 = [M[r][0] for r in range(W)]
+    add = []
+    for r in range(N_ROUNDS):
+        if r < 3:
+            v = rc[12 * (r + 1) : 12 * (r + 2)]
+        elif r == 3:
+            v = params["fast_partial_first_round_constant"][:]
+        elif r < 26:
+            c = params["fast_partial_round_constants"][r - 4]
+            v = [c * col0[i] % P for i in range(W)]
+            if r == 25:
+                v = [(v[i] + rc[12 * 26 + i]) % P for i in range(W)]
+        elif r < 29:
+            v = rc[12 * (r + 1) : 12 * (r + 2)]
+        else:
+            v = [0] * W
+        add.append([x % P for x in v])
+    return add
+
+
+def poseidon_unified(params, add, state):
+    rc = params["all_round_constants"]
+    M = mds_matrix(params)
+    s = [(state[i] + rc[i]) % P for i in range(W)]
+    for r in range(N_ROUNDS):
+        if r < 4 or r >= 26:
+            s = [pow(x, 7, P) for x in s]
+        else:
+            s[0] = pow(s[0], 7, P)
+        s = mat_vec(M, s)
+        s = [(s[i] + add[r][i]) % P for i in range(W)]
+    return s
+
+
 def mds_network(circ, s):
     """Add/shift network for y_r = sum_i circ[i] * s[(r+i) % 12] on integers (csrc/poseidon.cuh:mds_half).
     x^12 - 1 = prod_{zeta^4=1} (x^3 - zeta): 4-point DFTs of the three stride-3 subsequences, one
@@ -414,7 +461,7 @@ def c_array(name, vals, per_line=4, ctype="uint64_t", qual="static const"):
     return "\n".join(out)
 
 
-def write_headers(params, C):
+def write_headers(params, C, add):
     banner = (
         "// GENERATED by tests/golden/make_golden.py from tests/golden/poseidon_params.json -- do not edit.\n"
         "// Poseidon-12 / Goldilocks parameters (data, scraped from the reference:\n"
@@ -438,6 +485,8 @@ def write_headers(params, C):
     h = [banner, "#pragma once", "#include <stdint.h>", ""]
     h.append("namespace pcs { namespace pconst {")
     h.append(c_array("RC", params["all_round_constants"], qual=q))
+    h.append("// ROUND_ADD[12*r + i]: see make_golden.round_addends (constants moved behind the linear layer)")
+    h.append(c_array("ROUND_ADD", [x for row in add for x in row], qual=q))
     h.append(c_array("FIRST_RC", params["fast_partial_first_round_constant"], qual=q))
     h.append(c_array("PARTIAL_RC", params["fast_partial_round_constants"], qual=q))
     h.append(c_array("VS", params["fast_partial_round_vs"], qual=q))
@@ -473,6 +522,9 @@ def main():
     mds_network_check(params)
     for kv in kat["poseidon12_kats"]:
         assert poseidon_dense_partial(params, kv["input"]) == kv["output"], "dense-partial KAT mismatch"
+    add = round_addends(params)
+    for kv in kat["poseidon12_kats"]:
+        assert poseidon_unified(params, add, kv["input"]) == kv["output"], "unified-loop KAT mismatch"
     # 3. lazy partial-round tables agree too
     C = derive_lazy_tables(params)
     import random
@@ -493,7 +545,7 @@ def main():
         json.dump(params, f, indent=0)
     with open(os.path.join(HERE, "reference_kats.json"), "w") as f:
         json.dump(kat, f, indent=0)
-    write_headers(params, C)
+    write_headers(params, C, add)
     print("golden fixtures + headers written; derived FAST_* tables match the reference")
 
 
