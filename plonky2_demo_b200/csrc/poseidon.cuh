@@ -29,6 +29,9 @@
 
 namespace pcs {
 
+#ifndef PCS_MDS_FP64
+#define PCS_MDS_FP64 1
+#endif
 #ifndef PCS_SBOX_GROUP
 #define PCS_SBOX_GROUP 12
 #endif
@@ -101,6 +104,85 @@ __device__ __forceinline__ void mds_layer(uint64_t (&s)[12], const uint64_t* __r
     for (int r = 0; r < 12; r++) s[r] = gl::fold_halves(L[r], H[r]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same network on the FP64 pipe.
+//
+// B200 has a full-rate FP64 pipe (measured 61 DFMA/clk/SM, co-issuing with the integer pipes at
+// 121 instr/clk/SM, profiles/r01_fp64pipe.md) that integer code leaves idle, while the integer
+// version of the network saturates the ALU pipe (profiles/r01_poseidon_unified.md).  Every value in
+// the network is an integer of magnitude < 2^45 and every operation is an add, a subtract or a
+// multiplication by 2, 4, 8 or 16 -- all EXACT in IEEE double (53-bit significand), in any
+// evaluation order and rounding mode.  One DADD/DFMA replaces the IADD3 + IADD3.X pair of a 64-bit
+// integer add, and fused shift-adds are free.
+//   in : a 32-bit half x enters as the double with bit pattern 0x43300000_xxxxxxxx = 2^52 + x
+//        (no conversion instruction); differences of two such values are exact, and
+//        (2^52 + x) - 2^52 recovers x where a sum needs it.
+//   out: the last addition adds the pre-biased round constant 2^52 + c (ROUND_ADD_D), so the result
+//        2^52 + y has y's low 32 bits in its low word and y >> 32 in its high word - 0x43300000.
+// ------------------------------------------------------------------------------------------------
+constexpr double TWO52 = 4503599627370496.0;
+
+__device__ __forceinline__ void mds_half_fp64(const uint32_t (&s)[12], const double* __restrict__ addb /*stride 2*/,
+                                              uint32_t (&ylo)[12], uint32_t (&yhi)[12]) {
+    double A[3], B[3], P[3], Q[3];
+    double s0d;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        double v0 = __hiloint2double(0x43300000, (int)s[j]), v3 = __hiloint2double(0x43300000, (int)s[j + 3]);
+        double v6 = __hiloint2double(0x43300000, (int)s[j + 6]), v9 = __hiloint2double(0x43300000, (int)s[j + 9]);
+        double d6 = v6 - TWO52, d9 = v9 - TWO52;  // s6, s9 as exact doubles
+        P[j] = v0 - v6;                           // s0 - s6
+        Q[j] = v3 - v9;                           // s3 - s9
+        double u = fma(d6, 2.0, P[j]);            // s0 + s6
+        double v = fma(d9, 2.0, Q[j]);            // s3 + s9
+        A[j] = u + v;
+        B[j] = u - v;
+        if (j == 0) s0d = P[0] + d6;              // s0 itself, for the diagonal term
+    }
+    double t = A[0] + A[1] + A[2];
+    double Ya[3] = {t + A[2], t + A[0], t + A[1]};  // times 16, applied below
+    double Yb[3] = {fma(B[1], -2.0, fma(B[2], 8.0, -B[0])),
+                    fma(B[2], -2.0, fma(B[0], -8.0, -B[1])),
+                    fma(B[1], -8.0, fma(B[0], 2.0, -B[2]))};
+    double re[3], im[3];
+    re[0] = fma(Q[2], 4.0, fma(Q[1], -16.0, fma(P[0], 2.0, -Q[0]) + P[1]) + P[2]);
+    im[0] = fma(P[2], -4.0, fma(P[1], 16.0, fma(Q[0], 2.0, P[0]) + Q[1]) + Q[2]);
+    re[1] = fma(Q[2], -16.0, fma(P[1], 2.0, fma(P[0], -4.0, Q[0]) - Q[1]) + P[2]);
+    im[1] = fma(P[2], 16.0, fma(Q[1], 2.0, fma(Q[0], -4.0, -P[0]) + P[1]) + Q[2]);
+    re[2] = fma(P[2], 2.0, fma(P[1], -4.0, fma(P[0], 16.0, Q[0]) + Q[1]) - Q[2]);
+    im[2] = fma(Q[2], 2.0, fma(Q[1], -4.0, fma(Q[0], 16.0, -P[0]) - P[1]) + P[2]);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        double e1 = fma(Ya[j], 16.0, Yb[j]), e2 = fma(Ya[j], 16.0, -Yb[j]);
+        double y0 = e1 + re[j];
+        if (j == 0) y0 = fma(s0d, 8.0, y0);       // MDS_MATRIX_DIAG[0] = 8
+        double r0 = y0 + addb[2 * j];
+        double r3 = (e2 + im[j]) + addb[2 * (j + 3)];
+        double r6 = (e1 - re[j]) + addb[2 * (j + 6)];
+        double r9 = (e2 - im[j]) + addb[2 * (j + 9)];
+        ylo[j] = (uint32_t)__double2loint(r0);     yhi[j] = (uint32_t)__double2hiint(r0);
+        ylo[j + 3] = (uint32_t)__double2loint(r3); yhi[j + 3] = (uint32_t)__double2hiint(r3);
+        ylo[j + 6] = (uint32_t)__double2loint(r6); yhi[j + 6] = (uint32_t)__double2hiint(r6);
+        ylo[j + 9] = (uint32_t)__double2loint(r9); yhi[j + 9] = (uint32_t)__double2hiint(r9);
+    }
+}
+
+// s <- MDS * s + ROUND_ADD[r]  on the FP64 pipe; rcd = &ROUND_ADD_D[24 * r]
+__device__ __forceinline__ void mds_layer_fp64(uint64_t (&s)[12], const uint64_t* __restrict__ rcd) {
+    const double* addb = reinterpret_cast<const double*>(rcd);
+    uint32_t lo[12], hi[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        lo[i] = (uint32_t)s[i];
+        hi[i] = (uint32_t)(s[i] >> 32);
+    }
+    uint32_t l0[12], l1[12], h0[12], h1[12];
+    mds_half_fp64(lo, addb, l0, l1);
+    mds_half_fp64(hi, addb + 1, h0, h1);
+#pragma unroll
+    for (int r = 0; r < 12; r++) s[r] = gl::fold_halves_biased(l0[r], l1[r], h0[r], h1[r]);
+}
+
 // The permutation.  Input lanes: any u64 (loose); output lanes: canonical.
 //
 // ONE round loop for all 30 rounds (the body is ~22 KB of SASS and must stay resident in the SM's
@@ -136,7 +218,11 @@ __device__ __forceinline__ void poseidon12(uint64_t (&s)[12]) {
         } else {
             s[0] = sbox7(s[0]);
         }
+#if PCS_MDS_FP64
+        mds_layer_fp64(s, &ROUND_ADD_D[24 * r]);
+#else
         mds_layer<1>(s, &ROUND_ADD[12 * r]);
+#endif
     }
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl::canon(s[i]);

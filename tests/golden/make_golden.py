@@ -487,6 +487,16 @@ def write_headers(params, C, add):
     h.append(c_array("RC", params["all_round_constants"], qual=q))
     h.append("// ROUND_ADD[12*r + i]: see make_golden.round_addends (constants moved behind the linear layer)")
     h.append(c_array("ROUND_ADD", [x for row in add for x in row], qual=q))
+    # the same addends split in 32-bit halves and pre-biased as doubles 2^52 + half (bit pattern
+    # 0x43300000_hhhhhhhh): the FP64 MDS network adds them last, which also converts its exact
+    # integer result back to "integer in the mantissa" form for free.
+    biased = []
+    for row in add:
+        for x in row:
+            biased.append((0x43300000 << 32) | (x & 0xFFFFFFFF))
+            biased.append((0x43300000 << 32) | (x >> 32))
+    h.append("// ROUND_ADD_D[24*r + 2*i + {0,1}] = bits of the double 2^52 + {low, high} 32-bit half of ROUND_ADD[12*r + i]")
+    h.append(c_array("ROUND_ADD_D", biased, qual=q))
     h.append(c_array("FIRST_RC", params["fast_partial_first_round_constant"], qual=q))
     h.append(c_array("PARTIAL_RC", params["fast_partial_round_constants"], qual=q))
     h.append(c_array("VS", params["fast_partial_round_vs"], qual=q))
