@@ -55,7 +55,7 @@ def build(force=False, verbose=False, extra=()):
         res = list(ex.map(lambda s: _compile(s, force, list(extra)), srcs))
     objs = [o for o, _ in res]
     changed = any(c for _, c in res)
-    if changed or not os.path.exists(LIB):
+    if changed or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         cmd = [NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:

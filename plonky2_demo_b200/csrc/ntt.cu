@@ -38,7 +38,7 @@ namespace pcs {
 
 constexpr int NTT_MAX_NB = 10;          // stages per pass
 constexpr int NTT_TILE_LOG = 13;        // 8192 elements (64 KiB) per tile
-constexpr int NTT_THREADS = 512;
+constexpr int NTT_THREADS = 256;          // x 32 registers = one tile
 
 struct NttPass {
     unsigned s0, nb;   // stages [s0, s0+nb)
@@ -148,7 +148,19 @@ void ntt_plans_free() {
 }
 
 // -------------------------------------------------------------------------------------------------
-// the pass kernel
+// the pass kernel (register-blocked)
+//
+// A tile is 2^13 elements = R x C, R = 2^nb rows (the nb index bits this pass transforms), C columns
+// (2^lcl contiguous low index bits x 2^(lc-lcl) polynomials).  Tile coordinate, in memory order:
+//       E = [ pcol | rho (nb bits) | lcol (lcl bits) ]                      (13 bits)
+// 256 threads x 32 registers.  The nb stages run as (at most) two register ROUNDS of K1 and K2 stages:
+// in a round a thread owns all 2^K values of a K-bit field of rho (and 2^(5-K) polynomials) and does
+// the K stages on registers; between the two rounds the tile goes once through shared memory.
+// Stages inside a round use a constant-geometry butterfly (pairs (j, j+16), results to (2j, 2j+1)),
+// so the stage loop is rolled: ~12 KB of SASS instead of 50 KB, and register indices stay static.
+// Twiddles of one (coset, high bits) prefix G are built once per CTA in shared memory, replicated
+// per butterfly slot so that every twiddle load is [thread base + immediate]; a CTA then walks
+// several column groups (tiles) with the same G.
 // -------------------------------------------------------------------------------------------------
 struct PassArgs {
     const uint64_t* in;
@@ -158,96 +170,161 @@ struct PassArgs {
     const uint64_t* gamma;
     const uint64_t* psi;
     uint32_t n_polys;
-    uint32_t r, s0, nb, L, lg_d;
-    uint32_t lc;        // log2(columns per tile)
-    uint32_t lcl;       // log2(columns per tile taken from the low index bits) = min(L, lc)
-    uint32_t col_groups_per_poly_block;  // 2^(L - lcl)
-    uint64_t scale;     // multiply outputs (last pass of the inverse transform), 1 = none
-    int canon_in;       // canonicalise inputs (first pass reads caller data)
+    uint32_t r, s0, L, lg_d;
+    uint32_t lcl;              // log2(columns per tile taken from the low index bits)
+    uint32_t lgroups;          // 2^(L - lcl) column groups per block of polynomials
+    uint32_t n_cg;             // column groups in total (lgroups * poly groups)
+    uint32_t tiles_per_cta;
+    uint64_t scale;            // multiply outputs (last pass of the inverse transform), 1 = none
+    int last;                  // last pass: outputs leave the engine => canonical
 };
 
-// Tile element (row rho, column col) lives at smem[rho * pitch + col], pitch odd.
-__global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(const PassArgs a) {
-    extern __shared__ uint64_t smem[];
-    const uint32_t R = 1u << a.nb, C = 1u << a.lc;
-    const uint32_t pitch = C | 1u;
-    uint64_t* tw = smem;            // [R] (index 0 unused)
-    uint64_t* tile = smem + R;      // [R][pitch]
+__device__ __forceinline__ uint32_t sw(uint32_t E) { return E ^ ((E >> 5) & 31u); }
 
-    // ---- which tile ----
-    // 1-D grid, G fastest: neighbouring CTAs are the 2^r cosets of the same input tile (L2 reuse)
-    const uint32_t G = blockIdx.x & ((1u << (a.r + a.s0)) - 1);  // (coset, high bits) prefix, r + s0 bits
+// K stages on 32 registers; stage s pairs (j, j+16) with twiddle twp[s*16*STRIDE + j*STRIDE] and
+// rotates the register index left by one bit.
+template <int STRIDE>
+__device__ __forceinline__ void run_stages(uint64_t (&x)[32], const uint64_t* twp, int k) {
+#pragma unroll 1
+    for (int s = 0; s < k; s++, twp += 16 * STRIDE) {
+        uint64_t y[32];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            uint64_t t = gl::canon(gl::mul(x[j + 16], twp[j * STRIDE]));
+            y[2 * j] = gl::add_lc(x[j], t);
+            y[2 * j + 1] = gl::sub_lc(x[j], t);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j++) x[j] = y[j];
+    }
+}
+
+template <int K1, int K2>
+__global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassArgs a) {
+    constexpr int NB = K1 + K2;
+    constexpr int LC = NTT_TILE_LOG - NB;
+    constexpr uint32_t TILE = 1u << NTT_TILE_LOG;
+    extern __shared__ uint64_t smem[];
+    uint64_t* tile = smem;                 // [TILE], swizzled by sw()
+    uint64_t* tw1 = tile + TILE;           // [K1][16]
+    uint64_t* tw2 = tw1 + 16 * K1;         // [K2][16][32]
+    uint64_t* gam = tw2 + 512 * K2;        // [NB]
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lcl = a.lcl;
+    const uint32_t PB = LC - lcl;          // polynomial bits of the tile coordinate
+
+    // ---- which prefix / which column groups ----
+    const uint32_t gbits = a.r + a.s0;
+    const uint32_t G = blockIdx.x & ((1u << gbits) - 1);   // G fastest: the 2^r cosets of an input tile are neighbours
     const uint32_t c = G >> a.s0, H = G & ((1u << a.s0) - 1);
-    const uint32_t cg = blockIdx.x >> (a.r + a.s0);               // column group
-    const uint32_t lgroup = cg % a.col_groups_per_poly_block;   // which slice of the low index bits
-    const uint32_t pgroup = cg / a.col_groups_per_poly_block;   // which block of polynomials
-    const uint32_t polys_per_tile = 1u << (a.lc - a.lcl);
-    const uint32_t l_base = lgroup << a.lcl;
-    const uint32_t poly_base = pgroup * polys_per_tile;
-    const size_t row_stride = (size_t)1 << a.L;
+    const uint32_t cg0 = (blockIdx.x >> gbits) * a.tiles_per_cta;
     const size_t h_off = (size_t)H << (a.lg_d - a.s0);
 
-    // ---- twiddles: tw[2^i + q] = gamma_i * psi[q] ----
-    {
-        uint64_t g = a.gamma[G];  // gamma_{nb-1}
-        // thread t computes entries of every stage where q = t is in range
-        for (int i = (int)a.nb - 1; i >= 0; i--) {
-            for (uint32_t q = threadIdx.x; q < (1u << i); q += blockDim.x) tw[(1u << i) + q] = gl::mul(g, a.psi[q]);
-            g = gl::sqr(g);
-        }
+    // ---- twiddles of this prefix: gam[i] = gamma_i, entry(stage i, q) = gamma_i * psi[q] ----
+    if (tid < NB) {
+        uint64_t g = a.gamma[G];  // gamma_{NB-1}
+        for (int i = NB - 1; i > (int)tid; i--) g = gl::sqr(g);
+        gam[tid] = g;
     }
-
-    // ---- load ----
-    const bool row_major_threads = (a.lcl == 0);  // columns are polynomials: make consecutive threads walk rows
-    for (uint32_t e = threadIdx.x; e < R * C; e += blockDim.x) {
-        uint32_t rho, col;
-        if (row_major_threads) { rho = e & (R - 1); col = e >> a.nb; }
-        else { col = e & (C - 1); rho = e >> a.lc; }
-        uint32_t lcol = col & ((1u << a.lcl) - 1), pcol = col >> a.lcl;
-        uint32_t poly = poly_base + pcol;
-        uint64_t v = 0;
-        if (poly < a.n_polys) {
-            size_t idx = (size_t)poly * a.in_poly_stride + (size_t)c * a.in_coset_stride + h_off +
-                         (size_t)rho * row_stride + l_base + lcol;
-            v = a.in[idx];
-            if (a.canon_in) v = gl::canon(v);
+    __syncthreads();
+    for (uint32_t e = tid; e < 16 * K1; e += NTT_THREADS) {
+        uint32_t s = e >> 4, j = e & 15;
+        tw1[e] = gl::canon(gl::mul(gam[s], a.psi[j & ((1u << s) - 1)]));
+    }
+    if (K2 > 0) {
+        for (uint32_t e = tid; e < (uint32_t)(K2 * 16) << K1; e += NTT_THREADS) {
+            uint32_t ra = e & ((1u << K1) - 1), j = (e >> K1) & 15, s = e >> (K1 + 4);
+            uint32_t q = (ra << s) | (j & ((1u << s) - 1));
+            tw2[(s * 16 + j) * 32 + ra] = gl::canon(gl::mul(gam[K1 + s], a.psi[q]));
         }
-        tile[rho * pitch + col] = v;
     }
     __syncthreads();
 
-    // ---- nb radix-2 stages in shared memory ----
-    for (uint32_t i = 0; i < a.nb; i++) {
-        const uint32_t lg_half = a.nb - 1 - i, half = 1u << lg_half;
-        for (uint32_t e = threadIdx.x; e < (R >> 1) * C; e += blockDim.x) {
-            uint32_t col, pr;
-            if (row_major_threads) { pr = e & ((R >> 1) - 1); col = e >> (a.nb - 1); }
-            else { col = e & (C - 1); pr = e >> a.lc; }
-            uint32_t q = pr >> lg_half, lowb = pr & (half - 1);
-            uint32_t r0 = (q << (lg_half + 1)) + lowb, r1 = r0 + half;
-            uint64_t w = tw[(1u << i) + q];
-            uint64_t u = tile[r0 * pitch + col];
-            uint64_t v = gl::mul(tile[r1 * pitch + col], w);
-            tile[r0 * pitch + col] = gl::add(u, v);
-            tile[r1 * pitch + col] = gl::sub(u, v);
-        }
-        __syncthreads();
-    }
+    // ---- per-thread coordinates (same for every tile) ----
+    // round 1: field = rho bits [NB-1 .. K2]; thread bits = [pcol_low | rho_lo (K2) | lcol]
+    const uint32_t lmask = (1u << lcl) - 1;
+    const uint32_t lcol1 = tid & lmask;
+    const uint32_t rlo1 = (tid >> lcl) & ((1u << K2) - 1);
+    const uint32_t pl1 = tid >> (lcl + K2);
+    const uint32_t xsh1 = PB - (5 - K1);                   // extras -> top polynomial bits
+    const uint32_t E1 = (pl1 << (NB + lcl)) | (rlo1 << lcl) | lcol1;
+    const uint32_t p1 = lcl + K2;
+    // round 2: field = rho bits [K2-1 .. 0]; thread bits = [pcol_low | rho_hi (K1) | lcol]
+    const uint32_t rhi2 = (tid >> lcl) & ((1u << K1) - 1);
+    const uint32_t pl2 = tid >> (lcl + K1);
+    const uint32_t xsh2 = PB - (5 - K2);
+    const uint32_t E2 = (pl2 << (NB + lcl)) | (rhi2 << (K2 + lcl)) | (tid & lmask);
+    const bool staged_out = K2 > 0 && lcl < 3;
 
-    // ---- store ----
-    for (uint32_t e = threadIdx.x; e < R * C; e += blockDim.x) {
-        uint32_t rho, col;
-        if (row_major_threads) { rho = e & (R - 1); col = e >> a.nb; }
-        else { col = e & (C - 1); rho = e >> a.lc; }
-        uint32_t lcol = col & ((1u << a.lcl) - 1), pcol = col >> a.lcl;
-        uint32_t poly = poly_base + pcol;
-        if (poly < a.n_polys) {
-            uint64_t v = tile[rho * pitch + col];
-            if (a.scale != 1) v = gl::mul(v, a.scale);
-            size_t idx = (size_t)poly * a.out_poly_stride + (size_t)c * a.out_coset_stride + h_off +
-                         (size_t)rho * row_stride + l_base + lcol;
-            a.out[idx] = v;
+    for (uint32_t ti = 0; ti < a.tiles_per_cta; ti++) {
+        const uint32_t cg = cg0 + ti;
+        if (cg >= a.n_cg) break;
+        const uint32_t lgroup = cg % a.lgroups, pgroup = cg / a.lgroups;
+        const uint32_t poly_base = pgroup << PB;
+        const size_t l_base = (size_t)lgroup << lcl;
+        const uint64_t* in_t = a.in + (size_t)c * a.in_coset_stride + h_off + l_base;
+        uint64_t* out_t = a.out + (size_t)c * a.out_coset_stride + h_off + l_base;
+
+        uint64_t x[32];
+        // ---- acquire round 1 straight from global memory ----
+        {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const uint32_t av = j >> (5 - K1), xv = j & ((1 << (5 - K1)) - 1);
+                const uint32_t poly = poly_base + pl1 + (xv << xsh1);
+                const size_t idx = (size_t)poly * a.in_poly_stride + ((size_t)((av << K2) | rlo1) << a.L) + lcol1;
+                x[j] = poly < a.n_polys ? in_t[idx] : 0;
+            }
         }
+        run_stages<1>(x, tw1, K1);
+        if (K2 > 0) {
+            // after K1 rotations register m holds field value m & (2^K1-1), extra m >> K1
+#pragma unroll
+            for (int m = 0; m < 32; m++) {
+                const uint32_t av = m & ((1 << K1) - 1), xv = m >> K1;
+                tile[sw(E1 + (av << p1) + (xv << (8 + K1)))] = x[m];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const uint32_t av = j >> (5 - K2), xv = j & ((1 << (5 - K2)) - 1);
+                x[j] = tile[sw(E2 + (av << lcl) + (xv << (8 + K2)))];
+            }
+            run_stages<32>(x, tw2 + rhi2, K2);
+        }
+        // ---- release ----
+        constexpr int KL = K2 > 0 ? K2 : K1;   // field width of the last round
+        if (a.last) {
+#pragma unroll
+            for (int m = 0; m < 32; m++) x[m] = gl::canon(a.scale != 1 ? gl::mul(x[m], a.scale) : x[m]);
+        }
+        if (staged_out) {
+            // the last round's field is the lowest index bits: regroup through shared memory so that
+            // a warp stores 256 contiguous bytes
+#pragma unroll
+            for (int m = 0; m < 32; m++) {
+                const uint32_t av = m & ((1 << KL) - 1), xv = m >> KL;
+                tile[sw(E2 + (av << lcl) + (xv << (8 + KL)))] = x[m];
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (uint32_t e = tid; e < TILE; e += NTT_THREADS) {
+                const uint32_t poly = poly_base + (e >> (NB + lcl));
+                // staged mode implies L == lcl: [rho | lcol] is contiguous in memory
+                if (poly < a.n_polys) out_t[(size_t)poly * a.out_poly_stride + (e & ((1u << (NB + lcl)) - 1))] = tile[sw(e)];
+            }
+        } else {
+            const uint32_t rbase = K2 > 0 ? (rhi2 << K2) : rlo1;   // K2 == 0: round-1 coordinates (rlo1 == 0)
+            const uint32_t plx = K2 > 0 ? pl2 : pl1, xshx = K2 > 0 ? xsh2 : xsh1, lc_ = K2 > 0 ? (tid & lmask) : lcol1;
+#pragma unroll
+            for (int m = 0; m < 32; m++) {
+                const uint32_t av = m & ((1 << KL) - 1), xv = m >> KL;
+                const uint32_t poly = poly_base + plx + (xv << xshx);
+                const size_t idx = (size_t)poly * a.out_poly_stride + ((size_t)(rbase | av) << a.L) + lc_;
+                if (poly < a.n_polys) out_t[idx] = x[m];
+            }
+        }
+        __syncthreads();   // the tile buffer is rewritten by the next iteration
     }
 }
 
@@ -257,7 +334,21 @@ __global__ void k_broadcast_const(const uint64_t* in, size_t in_stride, uint64_t
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w * n) return;
     size_t j = i / n, k = i % n;
-    out[j * out_stride + k] = gl::mul(gl::canon(in[j * in_stride]), scale);
+    out[j * out_stride + k] = gl::canon(gl::mul(gl::canon(in[j * in_stride]), scale));
+}
+
+typedef void (*pass_kernel_t)(const PassArgs);
+template <int K1, int K2>
+static cudaError_t launch_pass(const PassArgs& a, unsigned grid, cudaStream_t st) {
+    constexpr size_t smem = ((size_t)(1u << NTT_TILE_LOG) + 16 * K1 + 512 * K2 + 16) * sizeof(uint64_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_ntt_pass<K1, K2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    k_ntt_pass<K1, K2><<<grid, NTT_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
 }
 
 static cudaError_t run_passes(const NttPlan* plan, const uint64_t* in, size_t in_stride, uint64_t* out,
@@ -271,16 +362,11 @@ static cudaError_t run_passes(const NttPlan* plan, const uint64_t* in, size_t in
                                                                           plan->scale);
         return cudaGetLastError();
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     for (size_t pi = 0; pi < plan->passes.size(); pi++) {
         const NttPass& ps = plan->passes[pi];
         PassArgs a;
         bool first = pi == 0, last = pi + 1 == plan->passes.size();
+        const unsigned nb = ps.nb, k1 = nb <= 5 ? nb : (nb + 1) / 2, lc = NTT_TILE_LOG - nb;
         a.in = first ? in : out;
         a.out = out;
         a.in_poly_stride = first ? in_stride : out_stride;
@@ -290,21 +376,45 @@ static cudaError_t run_passes(const NttPlan* plan, const uint64_t* in, size_t in
         a.gamma = ps.gamma;
         a.psi = ps.psi;
         a.n_polys = (uint32_t)w;
-        a.r = r; a.s0 = ps.s0; a.nb = ps.nb; a.L = ps.L; a.lg_d = lg_d;
-        a.lc = NTT_TILE_LOG - ps.nb;
-        a.lcl = ps.L < a.lc ? ps.L : a.lc;
-        a.col_groups_per_poly_block = 1u << (ps.L - a.lcl);
-        a.scale = last ? plan->scale : 1;
-        a.canon_in = first ? 1 : 0;
-        uint32_t polys_per_tile = 1u << (a.lc - a.lcl);
+        a.r = r; a.s0 = ps.s0; a.L = ps.L; a.lg_d = lg_d;
+        // columns from the low index bits: at most L, at most lc, and few enough that a thread's
+        // round-2 twiddle row depends on its thread index only (lcl + k1 <= 8)
+        unsigned lcl = ps.L < lc ? ps.L : lc;
+        if (lcl > 8 - k1) lcl = 8 - k1;
+        a.lcl = lcl;
+        a.lgroups = 1u << (ps.L - lcl);
+        uint32_t polys_per_tile = 1u << (lc - lcl);
         uint32_t pgroups = (uint32_t)((w + polys_per_tile - 1) / polys_per_tile);
-        size_t n_blocks = ((size_t)a.col_groups_per_poly_block * pgroups) << (r + ps.s0);
+        size_t n_cg = (size_t)a.lgroups * pgroups;
+        if (n_cg > 0xffffffffULL) return cudaErrorInvalidConfiguration;
+        a.n_cg = (uint32_t)n_cg;
+        // enough CTAs for ~8 waves of 2 CTAs/SM, but amortise the twiddle build over up to 16 tiles
+        size_t total_tiles = n_cg << (r + ps.s0);
+        size_t tpc = total_tiles / (148 * 2 * 8);
+        if (tpc < 1) tpc = 1;
+        if (tpc > 32) tpc = 32;
+        if (tpc > n_cg) tpc = n_cg;
+        tpc = (n_cg + ((n_cg + tpc - 1) / tpc) - 1) / ((n_cg + tpc - 1) / tpc);   // even chunks
+        a.tiles_per_cta = (uint32_t)tpc;
+        a.scale = last ? plan->scale : 1;
+        a.last = last ? 1 : 0;
+        size_t n_blocks = ((n_cg + tpc - 1) / tpc) << (r + ps.s0);
         if (n_blocks > 0x7fffffffULL) return cudaErrorInvalidConfiguration;
-        dim3 grid((unsigned)n_blocks);
-        uint32_t R = 1u << ps.nb, C = 1u << a.lc;
-        size_t smem = (size_t)(R + R * (C | 1u)) * sizeof(uint64_t);
-        k_ntt_pass<<<grid, NTT_THREADS, smem, st>>>(a);
-        cudaError_t e = cudaGetLastError();
+        unsigned grid = (unsigned)n_blocks;
+        cudaError_t e;
+        switch (nb) {
+            case 1: e = launch_pass<1, 0>(a, grid, st); break;
+            case 2: e = launch_pass<2, 0>(a, grid, st); break;
+            case 3: e = launch_pass<3, 0>(a, grid, st); break;
+            case 4: e = launch_pass<4, 0>(a, grid, st); break;
+            case 5: e = launch_pass<5, 0>(a, grid, st); break;
+            case 6: e = launch_pass<3, 3>(a, grid, st); break;
+            case 7: e = launch_pass<4, 3>(a, grid, st); break;
+            case 8: e = launch_pass<4, 4>(a, grid, st); break;
+            case 9: e = launch_pass<5, 4>(a, grid, st); break;
+            case 10: e = launch_pass<5, 5>(a, grid, st); break;
+            default: e = cudaErrorInvalidConfiguration;
+        }
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;

@@ -86,11 +86,12 @@ def test_two_to_one(pcs):
 # ---------------------------------------------------------------------------------------------
 # NTT / LDE (reference properties: fft.rs:219-253, polynomial/mod.rs:478-518)
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("lg_n", [0, 1, 2, 3, 4, 7, 8, 10, 11, 13, 16])
+@pytest.mark.parametrize("lg_n", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22])
 def test_ntt_forward_inverse(pcs, lg_n):
+    # every pass-kernel instantiation (1..10 stages per pass) and the 1-, 2- and 3-pass plans
     from plonky2_demo_b200.polynomial import ntt_batch
 
-    w = 3 if lg_n > 12 else 9
+    w = 2 if lg_n > 16 else 3 if lg_n > 12 else 9
     rng = np.random.default_rng(lg_n)
     x = rng.integers(0, 1 << 64, size=(w, 1 << lg_n), dtype=np.uint64)  # non-canonical inputs allowed
     f = ntt_batch(x, inverse=False)
@@ -133,7 +134,7 @@ def test_coset_fft_and_lde_onto_coset(pcs):
     assert np.array_equal(lde1, oracle.coset_lde(c[None, :], 2, shift=1)[0])
 
 
-@pytest.mark.parametrize("lg_d,rate_bits,w", [(0, 3, 5), (1, 0, 4), (3, 3, 135), (5, 1, 7), (9, 3, 20), (10, 3, 9), (11, 2, 16), (12, 4, 3), (13, 3, 17), (15, 3, 6)])
+@pytest.mark.parametrize("lg_d,rate_bits,w", [(0, 3, 5), (1, 0, 4), (2, 2, 3), (3, 3, 135), (4, 0, 33), (5, 1, 7), (6, 3, 129), (7, 2, 70), (8, 1, 65), (9, 3, 20), (10, 3, 9), (11, 2, 16), (12, 4, 3), (13, 3, 17), (14, 1, 9), (15, 3, 6), (17, 2, 3), (18, 0, 2)])
 def test_coset_lde_layouts(pcs, lg_d, rate_bits, w):
     import ctypes as C
 
