@@ -14,8 +14,11 @@ batched Goldilocks coset LDE -> Poseidon leaf hashing -> Merkle levels up to the
   roofline     : dominant kernel (Poseidon leaf hashing) against the measured HBM peak
   cpu_baseline : the CPU oracle (C/OpenMP port of the reference algorithm) on a bounded sample
 
-N > 1 (torchrun, one rank per GPU): each rank commits its own batch (independent commitments,
-no data-path collective) -> weak scaling; value = all ranks' elems / max-over-ranks time.
+N > 1 (torchrun, one rank per GPU): the SAME commitment sharded over the N GPUs (BASELINE.json configs[3]:
+"... at 1/2/4/8 GPUs") -> strong scaling.  Rank r starts with its block of the 135 polynomials in HBM; a step is
+NCCL all-gather of the coefficients -> LDE of the rank's coset blocks (= a contiguous leaf range) -> leaf hashing
+-> the rank's cap subtrees -> NCCL all-gather of the cap (plonky2_demo_b200/sharded.py).
+value = W*N elems / max-over-ranks time.
 
 --impl reference times the CPU port of the reference (oracle/) with all host threads on a bounded
 sample of the same workload; rank 0 only.
@@ -36,6 +39,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 METRIC = "lde_merkle_commit_elems_per_s"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_hash_cols launch from an `ncu --set full` capture of this
+# very command, keyed by (width, lg_d, rate_bits, n_gpus); None where no capture exists.
+NCU_TRAFFIC = {}
+NCU_TRAFFIC_SOURCE = None
 UNIT = "elems/s"
 
 
@@ -209,33 +216,58 @@ def run_ours(a):
     d, n = 1 << lg_d, 1 << (lg_d + r)
     elems = w * n
 
-    # synthetic input: splitmix64(0x5EED0000 + j) stream per polynomial; every rank its own batch
-    host = torch.empty((w, d), dtype=torch.int64, pin_memory=True)
+    # synthetic input: splitmix64(0x5EED0000 + j) stream per polynomial.  world == 1: all W
+    # polynomials; world > 1: this rank's block of the same W polynomials (plonky2_demo_b200/sharded.py)
+    from plonky2_demo_b200.sharded import ShardedPolynomialBatch, ShardPlan
+
+    plan = ShardPlan(w, lg_d, r, cap_h, world)
+    p_lo, p_hi = plan.poly_range(rank) if world > 1 else (0, w)
+    w_loc = p_hi - p_lo
+    host = torch.empty((w_loc, d), dtype=torch.int64, pin_memory=True)
     host_np = host.numpy().view(np.uint64)
-    host_np[:] = seeded_polys(w, d, base_seed=0x5EED0000 + 1000 * rank)
+    from helpers import splitmix64_stream
+    for j in range(w_loc):
+        host_np[j] = splitmix64_stream(0x5EED0000 + p_lo + j, d)
     dev_coeffs = host.to(dev, non_blocking=False)
     cap_host = np.empty((1 << cap_h, 4), dtype=np.uint64)
-    dev_ptrs = _ffi.dev_ptr_array(dev_coeffs.data_ptr(), w, d)
-    host_ptrs = _ffi.ptr_array([host_np[j] for j in range(w)])
+    dev_ptrs = _ffi.dev_ptr_array(dev_coeffs.data_ptr(), w_loc, d)
+    host_ptrs = _ffi.ptr_array([host_np[j] for j in range(w_loc)])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    class _Sharded:
+        """adapter: free() like a raw handle"""
+        def __init__(self, b):
+            self.b = b
+
+    def free(h):
+        if isinstance(h, _Sharded):
+            h.b.free()
+        else:
+            L.pcs_batch_free(h)
+
     def commit_device():
+        if world > 1:
+            return _Sharded(ShardedPolynomialBatch.from_coeffs(dev_coeffs, w, r, cap_h, partitioned=True))
         h = C.c_void_p()
         _ffi.check(L.pcs_commit_from_coeffs(dev_ptrs, w, lg_d, r, cap_h, None, 0, _ffi.PCS_DEVICE_PTRS, None, C.byref(h)))
         return h
 
     def commit_host():
+        if world > 1:
+            b = ShardedPolynomialBatch.from_coeffs(host.to(dev, non_blocking=True), w, r, cap_h, partitioned=True)
+            cap_host[:] = b.cap
+            return _Sharded(b)
         h = C.c_void_p()
         _ffi.check(L.pcs_commit_from_coeffs(host_ptrs, w, lg_d, r, cap_h, None, 0, 0, _ffi.ptr(cap_host), C.byref(h)))
         return h
 
     # ---- warm-up (also builds twiddle tables, fills the memory pool) ----
     for _ in range(max(a.warmup, 3)):
-        L.pcs_batch_free(commit_device())
+        free(commit_device())
     barrier()
 
     # ---- timed: K device-resident commits ----
@@ -250,15 +282,18 @@ def run_ours(a):
     prev = None
     for _ in range(a.steps):
         if prev is not None:
-            L.pcs_batch_free(prev)   # stream-ordered free: the next commit reuses this HBM
-        prev = commit_device()       # asynchronous: enqueues LDE passes, leaf hashing, node levels
+            free(prev)               # stream-ordered free: the next commit reuses this HBM
+        prev = commit_device()       # world == 1: asynchronous (enqueues LDE passes, leaf hashing, node levels)
     e1.record(stream)
     barrier()
     t_wall1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
     cap_dev = np.empty((1 << cap_h, 4), dtype=np.uint64)
-    _ffi.check(L.pcs_batch_cap(prev, _ffi.ptr(cap_dev)))
-    L.pcs_batch_free(prev)
+    if world > 1:
+        cap_dev[:] = prev.b.cap
+    else:
+        _ffi.check(L.pcs_batch_cap(prev, _ffi.ptr(cap_dev)))
+    free(prev)
     ms5 = (C.c_float * 5)()
     ncommit = C.c_uint()
     _ffi.check(L.pcs_timing_totals(ms5, C.byref(ncommit), 1))
@@ -271,20 +306,20 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_per_step = ms_total / a.steps
-    value = world * elems * a.steps / (ms_total * 1e-3)
+    value = elems * a.steps / (ms_total * 1e-3)   # one commitment of W*N elements per step, whatever the GPU count
 
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
     e2e = None
     if not a.no_e2e:
         for _ in range(2):
-            L.pcs_batch_free(commit_host())
+            free(commit_host())
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
         tw0 = time.perf_counter()
         for _ in range(a.steps):
             h = commit_host()   # synchronous: returns once the cap is on the host
-            L.pcs_batch_free(h)
+            free(h)
         f1.record(stream)
         barrier()
         tw1 = time.perf_counter()
@@ -294,8 +329,8 @@ def run_ours(a):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_ms = float(te.item())
         assert np.array_equal(cap_host, cap_dev), "host-path and device-path caps differ"
-        e2e = {"value": world * elems * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": w * d * 8, "d2h_bytes_per_step": (1 << cap_h) * 32,
+        e2e = {"value": elems * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": w_loc * d * 8, "d2h_bytes_per_step": (1 << cap_h) * 32,
                "ms_per_step": e2e_ms / a.steps,
                "note": "pinned host coefficients -> pcs_commit_from_coeffs (host pointers) -> Merkle cap on host; "
                        "LDE rows and digests stay device-resident behind the batch handle"}
@@ -304,16 +339,19 @@ def run_ours(a):
     peaks, peak_src = measured_peaks()
     peak = float(peaks["hbm_gbs"])
     wt = w
-    leaf_bytes = wt * n * 8 + n * 32                       # read every LDE element once, write one digest per leaf
-    lde_bytes = w * d * 8 + w * n * 8                       # read coefficients, write LDE
-    node_bytes = 3 * 32 * (n - (1 << cap_h))                # each node: read 2 children, write 1 digest
-    commit_bytes = lde_bytes + 2 * (n - (1 << cap_h)) * 32 + (1 << cap_h) * 32
+    n_loc = n // world                                       # leaves hashed by one rank's launches
+    cap_loc = plan.local_cap_len() if world > 1 else (1 << cap_h)
+    leaf_bytes = wt * n_loc * 8 + n_loc * 32                 # read every LDE element once, write one digest per leaf
+    lde_bytes = w * d * 8 + w * n_loc * 8                    # read coefficients, write LDE
+    node_bytes = 3 * 32 * (n_loc - cap_loc)                  # each node: read 2 children, write 1 digest
+    commit_bytes = w * d * 8 + w * n * 8 + 2 * (n - (1 << cap_h)) * 32 + (1 << cap_h) * 32   # whole job
     leaf_ms, lde_ms, node_ms = phase[3], phase[1], phase[4]
-    n_perm_leaf = n * ((wt + 7) // 8) if wt > 4 else 0
-    n_perm_node = n - (1 << cap_h)
+    n_perm_leaf = n_loc * ((wt + 7) // 8) if wt > 4 else 0
+    n_perm_node = n_loc - cap_loc
     roofline = {"bound": "hbm", "kernel": "k_hash_cols (Poseidon leaf hashing, 17 permutations per 135-element leaf)",
                 "achieved": leaf_bytes / (leaf_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": leaf_bytes / (leaf_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "frac": leaf_bytes / (leaf_ms * 1e-3) / 1e9 / peak,
+                "traffic": NCU_TRAFFIC.get((w, lg_d, r, world)), "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": leaf_bytes, "launch_ms": leaf_ms,
                 "note": "integer-pipe bound, not HBM bound: see int_pipe"}
     sm_mhz = clocks.get("sm_mhz") or 1965.0
@@ -329,14 +367,15 @@ def run_ours(a):
     }
 
     lg_passes = (lg_d + 9) // 10 if lg_d else 1
-    launches_per_step = lg_passes + 1 + (lg_d + r - cap_h)
+    launches_per_step = lg_passes + 1 + (lg_d + r - cap_h)   # per rank: LDE passes + leaf hashing + node levels
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64 (Goldilocks field, integer)", "data": "synthetic",
-        "config": {"workload": workload_name(a), "elems_per_step_per_gpu": elems, "input_coeff_elems_per_s": value / (1 << r),
+        "config": {"workload": workload_name(a), "elems_per_step": elems, "input_coeff_elems_per_s": value / (1 << r),
                    "l2_policy": "inputs larger than L2 (1.13 GB coefficients, 9.06 GB LDE per step)",
-                   "parallelism": f"{world} independent commitments, one per GPU" if world > 1 else "single GPU"},
+                   "parallelism": (f"one commitment sharded over {world} GPUs by coset block (contiguous leaf ranges): NCCL all-gather of "
+                                   f"coefficients, per-rank LDE + hashing, NCCL all-gather of the cap") if world > 1 else "single GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
         "roofline": roofline, "int_pipe": int_pipe, "kernels": kernels,
         "phase_ms": {"IFFT": phase[0], "FFT + blinding": phase[1], "transpose LDEs": phase[2], "leaf hashing": phase[3], "node levels": phase[4]},

@@ -77,6 +77,9 @@ PCS_API int pcs_two_to_one(const uint64_t* left /*[n][4]*/, const uint64_t* righ
 /* fft_with_options(.., None, ..) / ifft_with_options on w polynomials, natural order in and out.
  *                                                                 field/src/fft.rs:57-65, 72-95       */
 PCS_API int pcs_ntt(uint64_t* polys /*[w][n] in/out*/, size_t w, unsigned lg_n, int inverse);
+/* The same transform in place on a DEVICE matrix [w][n] (natural order in and out), asynchronous on
+ * pcs_stream(): the per-GPU IFFT of a polynomial-partitioned from_values.                */
+PCS_API int pcs_ntt_dev(uint64_t* polys_dev, size_t w, unsigned lg_n, int inverse);
 /* PolynomialBatch::lde_values (no salts): p.lde(rate_bits).coset_fft_with_options(shift, Some(rate_bits), ..)
  * for every polynomial.                                           plonky2/src/fri/oracle.rs:100-118
  * layout 0: out[w][N] natural order (== the reference's Vec<Vec<F>>);
@@ -104,6 +107,19 @@ typedef struct pcs_batch pcs_batch;
 PCS_API int pcs_commit_from_coeffs(const uint64_t* const* polys, size_t w, unsigned lg_d, unsigned rate_bits,
                            unsigned cap_height, const uint64_t* const* salts, size_t salt_w, unsigned flags,
                            uint64_t* cap_out, pcs_batch** out);
+/* One SHARD of from_coeffs for a commitment spread over several GPUs (one process per GPU).
+ * In leaf order the LDE is 2^rate_bits coset blocks of d leaves each (block c = evaluations on the coset
+ * 7 * w_N^{brev(c)} <w_d>), so a contiguous leaf range [coset_first*d, (coset_first + 2^lg_cosets)*d) needs
+ * only the coefficients: this call extends exactly those cosets and builds the Merkle subtrees over them.
+ *   local_cap_height : cap height of the LOCAL tree = cap_height - log2(n_shards); the local cap is the
+ *                      slice cap[shard*2^local_cap_height ..] of the reference's cap, the local digests the
+ *                      matching contiguous slice of the reference's digests (merkle_tree.rs:43-46).
+ *   salts            : NULL, or salt_w pointers to the shard's d << lg_cosets salt values in LEAF order.
+ * The batch accessors then address leaves relative to the shard.                                     */
+PCS_API int pcs_commit_shard_from_coeffs(const uint64_t* const* polys, size_t w, unsigned lg_d, unsigned rate_bits,
+                                 unsigned coset_first, unsigned lg_cosets, unsigned local_cap_height,
+                                 const uint64_t* const* salts, size_t salt_w, unsigned flags, uint64_t* cap_out,
+                                 pcs_batch** out);
 /* PolynomialBatch::from_values: IFFT every column first.                         oracle.rs:43-65
  *   coeffs_out : NULL, or w host pointers receiving the d coefficients of each polynomial
  *                (the reference keeps them as `polynomials`).                                      */

@@ -21,6 +21,11 @@ struct Ctx {
     int device = -1;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // host-input pipeline: H2D copies run on their own stream, one event per chunk of polynomials,
+    // so that the LDE of chunk k overlaps the PCIe transfer of chunk k+1
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_sync = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
 };
 static Ctx g_ctx;
 
@@ -134,6 +139,9 @@ void pcs_shutdown(void) {
     cudaStreamSynchronize(g_ctx.stream);
     drain_pending();
     ntt_plans_free();
+    if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
+    if (g_ctx.ev_sync) cudaEventDestroy(g_ctx.ev_sync);
+    for (auto& e : g_ctx.chunk_ev) cudaEventDestroy(e);
     if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.stream);
     g_ctx = Ctx();
 }
@@ -215,10 +223,26 @@ int pcs_ntt(uint64_t* polys, size_t w, unsigned lg_n, int inverse) {
     PCS_CUDA(b.alloc(w * n * 8, st));
     PCS_CUDA(cudaMemcpyAsync(a.p, polys, w * n * 8, cudaMemcpyHostToDevice, st));
     PCS_CUDA(ntt_lde(plan, a.u64(), n, b.u64(), n, w, st));            // natural -> bit-reversed
-    PCS_CUDA(launch_bitrev_permute(b.u64(), n, a.u64(), n, w, lg_n, st));  // -> natural
+    PCS_CUDA(launch_bitrev_permute(b.u64(), n, a.u64(), n, w, lg_n, st, ntt_plan_scale(plan)));  // -> natural (+ 1/n)
     PCS_CUDA(cudaMemcpyAsync(polys, a.p, w * n * 8, cudaMemcpyDeviceToHost, st));
     PCS_CUDA(cudaStreamSynchronize(st));
     return PCS_OK;
+}
+
+int pcs_ntt_dev(uint64_t* polys_dev, size_t w, unsigned lg_n, int inverse) {
+    PCS_NEED_INIT();
+    if (w == 0) return PCS_OK;
+    if (!polys_dev) return fail(PCS_ERR_ARG, "polys is NULL");
+    if (lg_n > 32) return fail(PCS_ERR_TWO_ADICITY, "n_log <= TWO_ADICITY violated");
+    cudaStream_t st = g_ctx.stream;
+    size_t n = (size_t)1 << lg_n;
+    NttPlan* plan = ntt_plan_get(lg_n, 0, inverse != 0, 1, st);
+    if (!plan) return fail(PCS_ERR_ALLOC, "twiddle table allocation failed");
+    DevBuf b;
+    PCS_CUDA(b.alloc(w * n * 8, st));
+    PCS_CUDA(ntt_lde(plan, polys_dev, n, b.u64(), n, w, st));                                              // -> bit-reversed
+    PCS_CUDA(launch_bitrev_permute(b.u64(), n, polys_dev, n, w, lg_n, st, ntt_plan_scale(plan)));          // -> natural
+    return PCS_OK;   // asynchronous on pcs_stream()
 }
 
 // gather w separately allocated host/device polynomials into one [w][d] device matrix
@@ -320,22 +344,29 @@ void pcs_batch_free(pcs_batch* b) {
     delete b;
 }
 
+// shard == true: only the cosets [coset_first, coset_first + 2^lg_cosets) (leaf order) are extended and the
+// tree is built over those d << lg_cosets leaves with `cap_height` (the caller's LOCAL cap height); salts are
+// then the shard's rows, already in leaf order.
 static int commit_common(const uint64_t* const* polys, bool from_values, size_t w, unsigned lg_d, unsigned rate_bits,
                          unsigned cap_height, const uint64_t* const* salts, size_t salt_w, unsigned flags,
-                         uint64_t* const* coeffs_out, uint64_t* cap_out, pcs_batch** out) {
+                         uint64_t* const* coeffs_out, uint64_t* cap_out, pcs_batch** out, bool shard = false,
+                         unsigned coset_first = 0, unsigned lg_cosets = 0) {
     PCS_NEED_INIT();
     if (!out) return fail(PCS_ERR_ARG, "out is NULL");
     *out = nullptr;
     if (w == 0 || !polys) return fail(PCS_ERR_ARG, "empty batch (oracle.rs:76 polynomials[0])");
     if (salt_w && !salts) return fail(PCS_ERR_ARG, "salts is NULL");
-    unsigned lg_n = lg_d + rate_bits;
-    if (lg_n > 32) return fail(PCS_ERR_TWO_ADICITY, "n_log <= TWO_ADICITY violated");
+    if (lg_d + rate_bits > 32) return fail(PCS_ERR_TWO_ADICITY, "n_log <= TWO_ADICITY violated");
+    if (!shard) lg_cosets = rate_bits;
+    if (lg_cosets > rate_bits || ((size_t)coset_first + ((size_t)1 << lg_cosets)) > ((size_t)1 << rate_bits))
+        return fail(PCS_ERR_ARG, "coset range outside [0, 2^rate_bits)");
+    unsigned lg_n = lg_d + lg_cosets;   // leaves of this (shard of the) tree
     if (cap_height > lg_n)
         return fail(PCS_ERR_CAP_HEIGHT, "cap_height=" + std::to_string(cap_height) +
                                             " should be at most log2(leaves.len())=" + std::to_string(lg_n));
     cudaStream_t st = g_ctx.stream;
     const bool dev_ptrs = flags & PCS_DEVICE_PTRS;
-    const size_t d = (size_t)1 << lg_d, n = d << rate_bits, wt = w + salt_w;
+    const size_t d = (size_t)1 << lg_d, n = d << lg_cosets, wt = w + salt_w;
     const size_t n_cap = (size_t)1 << cap_height;
 
     NttPlan* plan = ntt_plan_get(lg_d, rate_bits, false, 7 /* F::coset_shift(), types.rs:437 */, st);
@@ -343,7 +374,7 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
     if (!plan || (from_values && !iplan)) return fail(PCS_ERR_ALLOC, "twiddle table allocation failed");
 
     pcs_batch* b = new pcs_batch();
-    b->w = w; b->salt_w = salt_w; b->lg_d = lg_d; b->rate_bits = rate_bits; b->cap_height = cap_height;
+    b->w = w; b->salt_w = salt_w; b->lg_d = lg_d; b->rate_bits = lg_cosets; b->cap_height = cap_height;
     b->n = n; b->n_digests = 2 * (n - n_cap); b->has_ifft = from_values;
     struct Guard { pcs_batch* b; bool armed = true; ~Guard() { if (armed) pcs_batch_free(b); } } guard{b};
     for (auto& e : b->ev) PCS_CUDA(cudaEventCreate(&e));
@@ -357,6 +388,8 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
         for (size_t j = 0; j < w; j++) contiguous_dev = contiguous_dev && polys[j] == polys[0] + j * d;
     const uint64_t* src = nullptr;   // [w][d] device input (values or coefficients)
     uint64_t* staged = nullptr;
+    constexpr size_t H2D_CHUNK = 16;  // polynomials per H2D chunk
+    size_t n_chunks = 0;              // > 0: host inputs arrive chunk by chunk on the copy stream
     if (contiguous_dev && !from_values && !(flags & PCS_KEEP_COEFFS)) {
         src = polys[0];
     } else {
@@ -364,9 +397,32 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
         b->coeffs = staged;  // owned by the batch from here on
         if (contiguous_dev)
             PCS_CUDA(cudaMemcpyAsync(staged, polys[0], w * d * 8, cudaMemcpyDeviceToDevice, st));
-        else {
-            int rc = stage_polys(polys, w, d, dev_ptrs, staged, st);
+        else if (dev_ptrs) {
+            int rc = stage_polys(polys, w, d, true, staged, st);
             if (rc) return rc;
+        } else {
+            // host inputs: chunked H2D on the copy stream, one event per chunk
+            if (!g_ctx.copy_stream) PCS_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
+            if (!g_ctx.ev_sync) PCS_CUDA(cudaEventCreateWithFlags(&g_ctx.ev_sync, cudaEventDisableTiming));
+            n_chunks = (w + H2D_CHUNK - 1) / H2D_CHUNK;
+            while (g_ctx.chunk_ev.size() < n_chunks) {
+                cudaEvent_t e;
+                PCS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                g_ctx.chunk_ev.push_back(e);
+            }
+            PCS_CUDA(cudaEventRecord(g_ctx.ev_sync, st));               // `staged` exists from here on
+            PCS_CUDA(cudaStreamWaitEvent(g_ctx.copy_stream, g_ctx.ev_sync, 0));
+            for (size_t k = 0; k < n_chunks; k++) {
+                size_t j0 = k * H2D_CHUNK, j1 = j0 + H2D_CHUNK < w ? j0 + H2D_CHUNK : w;
+                int rc = stage_polys(polys + j0, j1 - j0, d, false, staged + j0 * d, g_ctx.copy_stream);
+                if (rc) {
+                    cudaStreamSynchronize(g_ctx.copy_stream);   // `staged` is released by the guard
+                    return rc;
+                }
+                PCS_CUDA(cudaEventRecord(g_ctx.chunk_ev[k], g_ctx.copy_stream));
+            }
+            if (from_values)   // the IFFT below runs over the whole batch
+                PCS_CUDA(cudaStreamWaitEvent(st, g_ctx.chunk_ev[n_chunks - 1], 0));
         }
         src = staged;
     }
@@ -376,7 +432,7 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
     if (from_values) {
         // values (natural) -> coefficients in bit-reversed order (scratch = head of the LDE buffer)
         PCS_CUDA(ntt_inverse_bitrev(iplan, src, d, b->lde, d, w, st));
-        PCS_CUDA(launch_bitrev_permute(b->lde, d, staged, d, w, lg_d, st));  // -> natural order, in `staged`
+        PCS_CUDA(launch_bitrev_permute(b->lde, d, staged, d, w, lg_d, st, ntt_plan_scale(iplan)));  // -> natural order (+ 1/d), in `staged`
         if (coeffs_out)
             for (size_t j = 0; j < w; j++)
                 if (coeffs_out[j])
@@ -385,7 +441,15 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
     PCS_CUDA(cudaEventRecord(b->ev[1], st));
 
     // ---- "FFT + blinding" (oracle.rs:100-125), output already in leaf order ----
-    PCS_CUDA(ntt_lde(plan, src, d, b->lde, n, w, st));
+    if (n_chunks && !from_values) {
+        for (size_t k = 0; k < n_chunks; k++) {
+            size_t j0 = k * H2D_CHUNK, j1 = j0 + H2D_CHUNK < w ? j0 + H2D_CHUNK : w;
+            PCS_CUDA(cudaStreamWaitEvent(st, g_ctx.chunk_ev[k], 0));
+            PCS_CUDA(ntt_lde_cosets(plan, src + j0 * d, d, b->lde + j0 * n, n, j1 - j0, coset_first, lg_cosets, st));
+        }
+    } else {
+        PCS_CUDA(ntt_lde_cosets(plan, src, d, b->lde, n, w, coset_first, lg_cosets, st));
+    }
     for (size_t k = 0; k < salt_w; k++) {
         if (!salts[k]) return fail(PCS_ERR_ARG, "NULL salt pointer");
         // the caller's salt column k is in natural LDE order like lde_values (oracle.rs:119-123);
@@ -394,7 +458,10 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
         PCS_CUDA(tmp.alloc(n * 8, st));
         PCS_CUDA(cudaMemcpyAsync(tmp.p, salts[k], n * 8, dev_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
         PCS_CUDA(launch_canonicalize(tmp.u64(), n, st));
-        PCS_CUDA(launch_bitrev_permute(tmp.u64(), n, b->lde + (w + k) * n, n, 1, lg_n, st));
+        if (shard)   // already in leaf order
+            PCS_CUDA(cudaMemcpyAsync(b->lde + (w + k) * n, tmp.p, n * 8, cudaMemcpyDeviceToDevice, st));
+        else
+            PCS_CUDA(launch_bitrev_permute(tmp.u64(), n, b->lde + (w + k) * n, n, 1, lg_n, st));
     }
     PCS_CUDA(cudaEventRecord(b->ev[2], st));
     // "transpose LDEs" (oracle.rs:83): fused away -- the hash kernel reads columns directly
@@ -425,6 +492,14 @@ int pcs_commit_from_coeffs(const uint64_t* const* polys, size_t w, unsigned lg_d
                            unsigned cap_height, const uint64_t* const* salts, size_t salt_w, unsigned flags,
                            uint64_t* cap_out, pcs_batch** out) {
     return commit_common(polys, false, w, lg_d, rate_bits, cap_height, salts, salt_w, flags, nullptr, cap_out, out);
+}
+
+int pcs_commit_shard_from_coeffs(const uint64_t* const* polys, size_t w, unsigned lg_d, unsigned rate_bits,
+                                 unsigned coset_first, unsigned lg_cosets, unsigned local_cap_height,
+                                 const uint64_t* const* salts, size_t salt_w, unsigned flags, uint64_t* cap_out,
+                                 pcs_batch** out) {
+    return commit_common(polys, false, w, lg_d, rate_bits, local_cap_height, salts, salt_w, flags, nullptr, cap_out, out,
+                         true, coset_first, lg_cosets);
 }
 
 int pcs_commit_from_values(const uint64_t* const* values, size_t w, unsigned lg_d, unsigned rate_bits,

@@ -61,12 +61,19 @@ void ntt_plans_free();
 // (bit-reversed) order: out[j][c*d + t] = P_j(shift * w_N^{brev_r(c)} * w_d^{brev(t)}).
 cudaError_t ntt_lde(const NttPlan* plan, const uint64_t* coeffs, size_t in_stride, uint64_t* out,
                     size_t out_stride, size_t w, cudaStream_t st);
-// Inverse NTT incl. 1/d scaling: values [w][d] natural order -> `out` in BIT-REVERSED order.
+// Same for the coset sub-range [coset_first, coset_first + 2^lg_cosets) in leaf order (shard commits):
+// out [w][d << lg_cosets].
+cudaError_t ntt_lde_cosets(const NttPlan* plan, const uint64_t* coeffs, size_t in_stride, uint64_t* out,
+                           size_t out_stride, size_t w, unsigned coset_first, unsigned lg_cosets, cudaStream_t st);
+// Inverse NTT WITHOUT the 1/d scaling: values [w][d] natural order -> `out` in BIT-REVERSED order; the
+// bit-reversal permutation that always follows applies ntt_plan_scale(plan).
 cudaError_t ntt_inverse_bitrev(const NttPlan* plan, const uint64_t* values, size_t in_stride, uint64_t* out,
                                size_t out_stride, size_t w, cudaStream_t st);
 // out[j][brev(i)] = in[j][i]
+// out[j][brev(i)] = in[j][i] * scale
 cudaError_t launch_bitrev_permute(const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride,
-                                  size_t w, unsigned lg_n, cudaStream_t st);
+                                  size_t w, unsigned lg_n, cudaStream_t st, uint64_t scale = 1);
+uint64_t ntt_plan_scale(const NttPlan* plan);
 // out[c][r] = in[r][c] for in [rows][cols] (row pitch in_pitch), out row pitch out_pitch
 cudaError_t launch_transpose(const uint64_t* in, size_t in_pitch, uint64_t* out, size_t out_pitch,
                              size_t rows, size_t cols, cudaStream_t st);

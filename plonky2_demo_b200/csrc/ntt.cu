@@ -51,7 +51,7 @@ struct NttPlan {
     unsigned lg_d, r;
     bool inverse;
     uint64_t shift;
-    uint64_t scale;  // applied in the last pass (1/d for the inverse transform, else 1)
+    uint64_t scale;  // 1/d for the inverse transform (applied by the bit-reversal permutation that follows), else 1
     std::vector<NttPass> passes;
 };
 
@@ -170,12 +170,12 @@ struct PassArgs {
     const uint64_t* gamma;
     const uint64_t* psi;
     uint32_t n_polys;
-    uint32_t r, s0, L, lg_d;
+    uint32_t r, s0, L, lg_d;   // r = log2(cosets computed by this launch)
+    uint32_t c0;               // first coset (leaf order) of this launch: shard commits compute a sub-range
     uint32_t lcl;              // log2(columns per tile taken from the low index bits)
     uint32_t lgroups;          // 2^(L - lcl) column groups per block of polynomials
     uint32_t n_cg;             // column groups in total (lgroups * poly groups)
     uint32_t tiles_per_cta;
-    uint64_t scale;            // multiply outputs (last pass of the inverse transform), 1 = none
     int last;                  // last pass: outputs leave the engine => canonical
 };
 
@@ -216,13 +216,13 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassArgs a) {
     // ---- which prefix / which column groups ----
     const uint32_t gbits = a.r + a.s0;
     const uint32_t G = blockIdx.x & ((1u << gbits) - 1);   // G fastest: the 2^r cosets of an input tile are neighbours
-    const uint32_t c = G >> a.s0, H = G & ((1u << a.s0) - 1);
+    const uint32_t c = G >> a.s0, H = G & ((1u << a.s0) - 1);   // c: coset index local to this launch
     const uint32_t cg0 = (blockIdx.x >> gbits) * a.tiles_per_cta;
     const size_t h_off = (size_t)H << (a.lg_d - a.s0);
 
     // ---- twiddles of this prefix: gam[i] = gamma_i, entry(stage i, q) = gamma_i * psi[q] ----
     if (tid < NB) {
-        uint64_t g = a.gamma[G];  // gamma_{NB-1}
+        uint64_t g = a.gamma[G + ((size_t)a.c0 << a.s0)];  // gamma_{NB-1} of the global (coset, high bits) prefix
         for (int i = NB - 1; i > (int)tid; i--) g = gl::sqr(g);
         gam[tid] = g;
     }
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassArgs a) {
         constexpr int KL = K2 > 0 ? K2 : K1;   // field width of the last round
         if (a.last) {
 #pragma unroll
-            for (int m = 0; m < 32; m++) x[m] = gl::canon(a.scale != 1 ? gl::mul(x[m], a.scale) : x[m]);
+            for (int m = 0; m < 32; m++) x[m] = gl::canon(x[m]);
         }
         if (staged_out) {
             // the last round's field is the lowest index bits: regroup through shared memory so that
@@ -352,10 +352,12 @@ static cudaError_t launch_pass(const PassArgs& a, unsigned grid, cudaStream_t st
 }
 
 static cudaError_t run_passes(const NttPlan* plan, const uint64_t* in, size_t in_stride, uint64_t* out,
-                              size_t out_stride, size_t w, cudaStream_t st) {
-    const unsigned lg_d = plan->lg_d, r = plan->r;
+                              size_t out_stride, size_t w, unsigned coset_first, unsigned lg_cosets, cudaStream_t st) {
+    const unsigned lg_d = plan->lg_d, r = lg_cosets;
     const size_t d = (size_t)1 << lg_d;
     if (w == 0) return cudaSuccess;
+    if (lg_cosets > plan->r || ((size_t)coset_first + ((size_t)1 << lg_cosets)) > ((size_t)1 << plan->r))
+        return cudaErrorInvalidValue;
     if (lg_d == 0) {
         size_t n = (size_t)1 << r;
         k_broadcast_const<<<(unsigned)((w * n + 255) / 256), 256, 0, st>>>(in, in_stride, out, out_stride, w, n,
@@ -377,6 +379,7 @@ static cudaError_t run_passes(const NttPlan* plan, const uint64_t* in, size_t in
         a.psi = ps.psi;
         a.n_polys = (uint32_t)w;
         a.r = r; a.s0 = ps.s0; a.L = ps.L; a.lg_d = lg_d;
+        a.c0 = coset_first;
         // columns from the low index bits: at most L, at most lc, and few enough that a thread's
         // round-2 twiddle row depends on its thread index only (lcl + k1 <= 8)
         unsigned lcl = ps.L < lc ? ps.L : lc;
@@ -396,7 +399,6 @@ static cudaError_t run_passes(const NttPlan* plan, const uint64_t* in, size_t in
         if (tpc > n_cg) tpc = n_cg;
         tpc = (n_cg + ((n_cg + tpc - 1) / tpc) - 1) / ((n_cg + tpc - 1) / tpc);   // even chunks
         a.tiles_per_cta = (uint32_t)tpc;
-        a.scale = last ? plan->scale : 1;
         a.last = last ? 1 : 0;
         size_t n_blocks = ((n_cg + tpc - 1) / tpc) << (r + ps.s0);
         if (n_blocks > 0x7fffffffULL) return cudaErrorInvalidConfiguration;
@@ -422,34 +424,44 @@ static cudaError_t run_passes(const NttPlan* plan, const uint64_t* in, size_t in
 
 cudaError_t ntt_lde(const NttPlan* plan, const uint64_t* coeffs, size_t in_stride, uint64_t* out, size_t out_stride,
                     size_t w, cudaStream_t st) {
-    return run_passes(plan, coeffs, in_stride, out, out_stride, w, st);
+    return run_passes(plan, coeffs, in_stride, out, out_stride, w, 0, plan->r, st);
+}
+
+cudaError_t ntt_lde_cosets(const NttPlan* plan, const uint64_t* coeffs, size_t in_stride, uint64_t* out,
+                           size_t out_stride, size_t w, unsigned coset_first, unsigned lg_cosets, cudaStream_t st) {
+    return run_passes(plan, coeffs, in_stride, out, out_stride, w, coset_first, lg_cosets, st);
 }
 
 cudaError_t ntt_inverse_bitrev(const NttPlan* plan, const uint64_t* values, size_t in_stride, uint64_t* out,
                                size_t out_stride, size_t w, cudaStream_t st) {
-    return run_passes(plan, values, in_stride, out, out_stride, w, st);
+    return run_passes(plan, values, in_stride, out, out_stride, w, 0, plan->r, st);
 }
 
 // -------------------------------------------------------------------------------------------------
 // data-movement helpers
 // -------------------------------------------------------------------------------------------------
+// out[j][brev(i)] = in[j][i] * scale   (scale = 1/d after an inverse transform, ifft_with_options fft.rs:88-93)
 __global__ void k_bitrev_permute(const uint64_t* __restrict__ in, size_t in_stride, uint64_t* __restrict__ out,
-                                 size_t out_stride, unsigned lg_n) {
+                                 size_t out_stride, unsigned lg_n, uint64_t scale) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t j = blockIdx.y;
     if (i >= ((size_t)1 << lg_n)) return;
     size_t bi = lg_n ? (size_t)(__brevll((unsigned long long)i) >> (64 - lg_n)) : 0;
-    out[j * out_stride + bi] = in[j * in_stride + i];
+    uint64_t v = in[j * in_stride + i];
+    if (scale != 1) v = gl::canon(gl::mul(v, scale));
+    out[j * out_stride + bi] = v;
 }
 
+uint64_t ntt_plan_scale(const NttPlan* plan) { return plan->scale; }
+
 cudaError_t launch_bitrev_permute(const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride, size_t w,
-                                  unsigned lg_n, cudaStream_t st) {
+                                  unsigned lg_n, cudaStream_t st, uint64_t scale) {
     if (w == 0) return cudaSuccess;
     size_t n = (size_t)1 << lg_n;
     for (size_t j0 = 0; j0 < w; j0 += 65535) {
         size_t wj = w - j0 < 65535 ? w - j0 : 65535;
         dim3 grid((unsigned)((n + 255) / 256), (unsigned)wj);
-        k_bitrev_permute<<<grid, 256, 0, st>>>(in + j0 * in_stride, in_stride, out + j0 * out_stride, out_stride, lg_n);
+        k_bitrev_permute<<<grid, 256, 0, st>>>(in + j0 * in_stride, in_stride, out + j0 * out_stride, out_stride, lg_n, scale);
     }
     return cudaGetLastError();
 }

@@ -1,0 +1,263 @@
+"""One commitment spread over the GPUs of a single box: one process per GPU, torch.distributed for the plumbing.
+
+The reference has no distributed path (one process, rayon); this is the north-star's
+"large commitments are sharded across a single 8xB200 box".  The partition follows from the leaf-order
+identity of the LDE (oracle.rs:83-84): after the row bit-reversal, leaves
+[c*d, (c+1)*d) are the evaluations of ALL polynomials on ONE coset 7*w_N^{brev(c)}*<w_d>.  So
+
+  * rank r of G owns the coset blocks [r*2^rate_bits/G, (r+1)*2^rate_bits/G) = a contiguous leaf range,
+    hence whole cap subtrees and a contiguous slice of the reference's `digests` (merkle_tree.rs:43-46);
+  * it needs every polynomial's d coefficients (W*d elements), never another rank's LDE output.
+
+Exchange steps (the only collectives on the path):
+  1. all-gather of the coefficients when the input is polynomial-partitioned (rank r holds a block of the
+     W polynomials, e.g. after a per-rank IFFT in from_values): W*d*8 bytes in total, 8x less than the
+     all-to-all of LDE rows a polynomial-partitioned LDE would need (9 GB at 135 x 2^20, rate 3);
+  2. all-gather of the local caps (2^cap_height * 32 bytes in total).
+When G > 2^cap_height the ranks' single roots are combined on every rank with two_to_one (log2 G - cap_height
+levels, a handful of permutations).
+
+The per-rank compute (IFFT of the local block, LDE of the local cosets, leaf hashing, node levels) is the
+CUDA engine (`pcs_ntt_dev`, `pcs_commit_shard_from_coeffs`).  The engine object is injectable so that the
+partition / collective logic can be exercised on CPU (gloo, world_size 2) in tests; the product never
+substitutes it.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from .polynomial import log2_strict, reverse_bits
+
+
+class ShardPlan:
+    """Who owns what for (w polys, d = 2^lg_d, rate_bits, cap_height) over `world` ranks."""
+
+    def __init__(self, w, lg_d, rate_bits, cap_height, world):
+        if world < 1 or world & (world - 1):
+            raise ValueError(f"world size must be a power of two, got {world}")
+        lg_w = log2_strict(world)
+        if lg_w > rate_bits:
+            raise ValueError(f"cannot shard 2^{rate_bits} coset blocks over {world} ranks (need world <= 2^rate_bits)")
+        if cap_height > lg_d + rate_bits:
+            raise ValueError(f"cap_height={cap_height} should be at most log2(leaves.len())={lg_d + rate_bits}")
+        self.w, self.lg_d, self.rate_bits, self.cap_height, self.world = w, lg_d, rate_bits, cap_height, world
+        self.lg_world = lg_w
+        self.lg_cosets = rate_bits - lg_w                     # coset blocks per rank (log2)
+        self.local_cap_height = max(cap_height - lg_w, 0)
+        self.top_levels = max(lg_w - cap_height, 0)           # levels combined from the ranks' roots
+        self.n_leaves = 1 << (lg_d + rate_bits)
+        self.local_leaves = self.n_leaves >> lg_w
+        self.w_max = -(-w // world)                           # block distribution of polynomials
+
+    def coset_first(self, rank):
+        return rank << self.lg_cosets
+
+    def leaf_range(self, rank):
+        return rank * self.local_leaves, (rank + 1) * self.local_leaves
+
+    def owner_of_leaf(self, leaf):
+        return leaf // self.local_leaves
+
+    def poly_range(self, rank):
+        lo = min(rank * self.w_max, self.w)
+        return lo, min(lo + self.w_max, self.w)
+
+    def local_cap_len(self):
+        return 1 << self.local_cap_height
+
+    def assemble_cap(self, local_caps, two_to_one):
+        """local_caps: [world][2^local_cap_height][4] in rank order -> the reference's cap [2^cap_height][4]."""
+        caps = np.asarray(local_caps, dtype=np.uint64).reshape(-1, 4)
+        for _ in range(self.top_levels):
+            caps = two_to_one(caps[0::2], caps[1::2])
+        return np.ascontiguousarray(caps)
+
+    def extend_proof(self, rank, local_siblings, roots, two_to_one):
+        """Siblings above the local root when world > 2^cap_height (roots: [world][4])."""
+        sib = [np.asarray(local_siblings, dtype=np.uint64).reshape(-1, 4)]
+        level = np.asarray(roots, dtype=np.uint64).reshape(-1, 4)
+        idx = rank
+        for _ in range(self.top_levels):
+            sib.append(level[idx ^ 1].reshape(1, 4))
+            level = two_to_one(level[0::2], level[1::2])
+            idx >>= 1
+        return np.concatenate(sib, axis=0)
+
+
+class CudaShardEngine:
+    """Per-rank compute through the C ABI (no CPU path)."""
+
+    def intt_local(self, values):
+        """values: torch CUDA int64 tensor [w_local][d], transformed in place (values -> coefficients)."""
+        if values.shape[0] == 0:
+            return
+        _ffi.check(_ffi.lib().pcs_ntt_dev(C.c_void_p(values.data_ptr()), values.shape[0], log2_strict(values.shape[1]), 1))
+
+    def commit_shard(self, coeffs, w, plan, rank, keep_handle=True):
+        """coeffs: torch CUDA int64 tensor [>= w][d] (contiguous).  Returns (handle, local cap [2^lch][4])."""
+        L = _ffi.lib()
+        d = coeffs.shape[1]
+        ptrs = _ffi.dev_ptr_array(coeffs.data_ptr(), w, d)
+        cap = np.empty((plan.local_cap_len(), 4), dtype=np.uint64)
+        h = C.c_void_p()
+        _ffi.check(L.pcs_commit_shard_from_coeffs(ptrs, w, plan.lg_d, plan.rate_bits, plan.coset_first(rank), plan.lg_cosets,
+                                                  plan.local_cap_height, None, 0, _ffi.PCS_DEVICE_PTRS, _ffi.ptr(cap), C.byref(h)))
+        return h, cap
+
+    def two_to_one(self, left, right):
+        from .hashing import PoseidonHash
+
+        return PoseidonHash.two_to_one_batch(np.ascontiguousarray(left), np.ascontiguousarray(right))
+
+    def get_rows(self, handle, local_indices, width):
+        idx = np.ascontiguousarray(np.asarray(local_indices, dtype=np.uint64))
+        out = np.empty((idx.shape[0], width), dtype=np.uint64)
+        _ffi.check(_ffi.lib().pcs_batch_get_rows(handle, _ffi.ptr(idx), idx.shape[0], _ffi.ptr(out)))
+        return out
+
+    def prove(self, handle, local_index, n_siblings):
+        sib = np.empty((n_siblings, 4), dtype=np.uint64)
+        _ffi.check(_ffi.lib().pcs_batch_prove(handle, int(local_index), _ffi.ptr(sib)))
+        return sib
+
+    def digests(self, handle, n_digests):
+        out = np.empty((n_digests, 4), dtype=np.uint64)
+        _ffi.check(_ffi.lib().pcs_batch_digests(handle, _ffi.ptr(out)))
+        return out
+
+    def free(self, handle):
+        _ffi.lib().pcs_batch_free(handle)
+
+
+class ShardedPolynomialBatch:
+    """PolynomialBatch (oracle.rs:30-37) whose leaves / digests are spread over the ranks of a process group.
+
+    `cap` is replicated on every rank and equals the reference's `merkle_tree.cap` bit for bit;
+    rank r holds leaves [r*N/G, (r+1)*N/G) and the matching slice of `digests`.
+    """
+
+    def __init__(self):
+        self._h = None
+
+    # ---- constructors (collective: every rank of `group` calls them) ---------------------------------
+    @classmethod
+    def from_coeffs(cls, local_coeffs, n_polys, rate_bits, cap_height, group=None, engine=None, partitioned=True):
+        """oracle.rs:68-98 over a process group.
+
+        partitioned=True : `local_coeffs` is this rank's block [poly_range(rank)][d] of the n_polys polynomials
+                           (torch int64 tensor on the rank's device, bit pattern = u64);
+        partitioned=False: every rank already holds all [n_polys][d] coefficients.
+        """
+        import torch
+        import torch.distributed as dist
+
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        engine = engine or CudaShardEngine()
+        d = int(local_coeffs.shape[1])
+        plan = ShardPlan(n_polys, log2_strict(d), rate_bits, cap_height, world)
+        if partitioned and world > 1:
+            lo, hi = plan.poly_range(rank)
+            if local_coeffs.shape[0] != hi - lo:
+                raise ValueError(f"rank {rank} must hold polynomials [{lo}, {hi}), got {local_coeffs.shape[0]} rows")
+            # exchange step 1: all-gather of the coefficient blocks (padded to w_max rows per rank; the
+            # block distribution leaves padding only after the last polynomial, so rows [0, w) stay contiguous)
+            full = torch.empty((world * plan.w_max, d), dtype=torch.int64, device=local_coeffs.device)
+            if hi - lo == plan.w_max:
+                mine = local_coeffs.contiguous()
+            else:
+                mine = torch.zeros((plan.w_max, d), dtype=torch.int64, device=local_coeffs.device)
+                mine[: hi - lo] = local_coeffs
+            dist.all_gather_into_tensor(full, mine, group=group)
+        else:
+            full = local_coeffs.contiguous()
+        self = cls()
+        self.plan, self.rank, self.world, self.group, self.engine = plan, rank, world, group, engine
+        self.degree_log, self.rate_bits, self.blinding, self.cap_height = plan.lg_d, rate_bits, False, cap_height
+        self.n_polys = n_polys
+        self._coeffs = full          # PolynomialBatch.polynomials (replicated)
+        self._h, local_cap = engine.commit_shard(full, n_polys, plan, rank)
+        # exchange step 2: all-gather of the local caps
+        if world > 1:
+            mine = torch.from_numpy(local_cap.view(np.int64)).to(full.device)
+            allc = torch.empty((world * mine.shape[0], 4), dtype=torch.int64, device=full.device)
+            dist.all_gather_into_tensor(allc, mine, group=group)
+            caps = allc.cpu().numpy().view(np.uint64).reshape(world, -1, 4)
+        else:
+            caps = local_cap[None]
+        self._local_caps = caps
+        self.cap = plan.assemble_cap(caps, engine.two_to_one)
+        return self
+
+    @classmethod
+    def from_values(cls, local_values, n_polys, rate_bits, cap_height, group=None, engine=None):
+        """oracle.rs:43-65 over a process group: each rank IFFTs its own block of the polynomials
+        (values are overwritten by coefficients), then from_coeffs."""
+        engine = engine or CudaShardEngine()
+        engine.intt_local(local_values)
+        return cls.from_coeffs(local_values, n_polys, rate_bits, cap_height, group, engine, partitioned=True)
+
+    # ---- accessors ---------------------------------------------------------------------------------
+    @property
+    def n_local_digests(self):
+        return 2 * (self.plan.local_leaves - self.plan.local_cap_len())
+
+    def local_digests(self):
+        """This rank's contiguous slice of the reference's `digests` (world <= 2^cap_height)."""
+        return self.engine.digests(self._h, self.n_local_digests)
+
+    def get_rows(self, leaf_indices):
+        """merkle_tree.leaves[i] for global leaf indices; every rank gets every row (collective)."""
+        import torch
+        import torch.distributed as dist
+
+        idx = np.asarray(list(leaf_indices), dtype=np.int64)
+        lo, hi = self.plan.leaf_range(self.rank)
+        mine = (idx >= lo) & (idx < hi)
+        rows = np.zeros((idx.shape[0], self.n_polys), dtype=np.uint64)
+        if mine.any():
+            rows[mine] = self.engine.get_rows(self._h, idx[mine] - lo, self.n_polys)
+        if self.world > 1:
+            t = torch.from_numpy(rows.view(np.int64)).to(self._coeffs.device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)   # disjoint owners: sum == select
+            rows = t.cpu().numpy().view(np.uint64)
+        return rows
+
+    def get_lde_values(self, index, step):
+        """oracle.rs:128-133"""
+        leaf = reverse_bits(index * step, self.degree_log + self.rate_bits)
+        return self.get_rows([leaf])[0]
+
+    def prove(self, leaf_index):
+        """MerkleTree::prove (merkle_tree.rs:173-207) for a global leaf index (collective)."""
+        import torch
+        import torch.distributed as dist
+
+        plan = self.plan
+        owner = plan.owner_of_leaf(leaf_index)
+        n_local = log2_strict(plan.local_leaves) - plan.local_cap_height
+        n_total = n_local + plan.top_levels
+        sib = np.zeros((n_total, 4), dtype=np.uint64)
+        if owner == self.rank:
+            local = self.engine.prove(self._h, leaf_index - plan.leaf_range(owner)[0], n_local) if n_local else np.zeros((0, 4), np.uint64)
+            sib[:] = plan.extend_proof(owner, local, self._local_caps.reshape(self.world, -1, 4)[:, 0], self.engine.two_to_one) \
+                if plan.top_levels else local
+        if self.world > 1:
+            t = torch.from_numpy(sib.view(np.int64)).to(self._coeffs.device)
+            dist.broadcast(t, src=dist.get_global_rank(self.group, owner) if self.group is not None else owner, group=self.group)
+            sib = t.cpu().numpy().view(np.uint64)
+        from .hashing import MerkleProof
+
+        return MerkleProof(sib)
+
+    def free(self):
+        if self._h is not None:
+            self.engine.free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

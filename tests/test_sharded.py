@@ -1,0 +1,224 @@
+"""Sharded commitment (plonky2_demo_b200/sharded.py): partition plan on CPU, the collective logic under
+gloo with world_size 2 (the per-rank compute is replaced by the ORACLE -- test-only engine), and, on a GPU,
+every shard of a commitment computed by the CUDA engine and assembled against the unsharded reference."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import seeded_polys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleShardEngine:
+    """Test double of CudaShardEngine: same interface, CPU oracle arithmetic on torch CPU tensors."""
+
+    def __init__(self):
+        self.batches = {}
+
+    @staticmethod
+    def _u64(t):
+        return t.numpy().view(np.uint64)
+
+    def intt_local(self, values):
+        if values.shape[0]:
+            self._u64(values)[:] = oracle.fft(self._u64(values), inverse=True)
+
+    def commit_shard(self, coeffs, w, plan, rank):
+        c = np.ascontiguousarray(self._u64(coeffs)[:w])
+        leaves = oracle.transpose_bitrev(oracle.coset_lde(c, plan.rate_bits))
+        lo, hi = plan.leaf_range(rank)
+        digests, cap = oracle.merkle_build(leaves[lo:hi], plan.local_cap_height)
+        h = len(self.batches) + 1
+        self.batches[h] = (np.ascontiguousarray(leaves[lo:hi]), digests, plan)
+        return h, cap
+
+    def two_to_one(self, l, r):
+        return oracle.two_to_one(np.ascontiguousarray(l), np.ascontiguousarray(r))
+
+    def get_rows(self, h, idx, width):
+        return self.batches[h][0][np.asarray(idx, dtype=np.int64)]
+
+    def prove(self, h, i, n):
+        leaves, digests, plan = self.batches[h]
+        return oracle.merkle_prove(digests, leaves.shape[0], plan.local_cap_height, int(i)).reshape(n, 4)
+
+    def digests(self, h, n):
+        return self.batches[h][1]
+
+    def free(self, h):
+        self.batches.pop(h, None)
+
+
+# ---------------------------------------------------------------------------------------------
+# plan (pure host logic)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,lg_d,r,cap,world", [(135, 20, 3, 4, 8), (135, 20, 3, 4, 2), (20, 5, 3, 4, 8), (7, 4, 2, 0, 4), (5, 3, 3, 1, 8), (3, 2, 1, 3, 1)])
+def test_shard_plan_partitions(w, lg_d, r, cap, world):
+    from plonky2_demo_b200.sharded import ShardPlan
+
+    p = ShardPlan(w, lg_d, r, cap, world)
+    # polynomials: contiguous blocks covering [0, w) exactly once, padding only at the end
+    got = [p.poly_range(k) for k in range(world)]
+    assert got[0][0] == 0 and got[-1][1] == w
+    assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
+    assert all(hi - lo <= p.w_max for lo, hi in got)
+    full = [k for k, (lo, hi) in enumerate(got) if hi - lo == p.w_max]
+    assert full == list(range(len(full)))  # full blocks first => gathered rows [0, w) are contiguous
+    # leaves / cosets: contiguous, disjoint, whole coset blocks
+    assert [p.leaf_range(k) for k in range(world)] == [(k * p.n_leaves // world, (k + 1) * p.n_leaves // world) for k in range(world)]
+    assert p.coset_first(world - 1) + (1 << p.lg_cosets) == 1 << r
+    assert p.local_leaves == (1 << lg_d) << p.lg_cosets
+    assert (p.local_cap_len() * world) >> p.top_levels == 1 << cap
+
+
+def test_shard_plan_rejects():
+    from plonky2_demo_b200.sharded import ShardPlan
+
+    with pytest.raises(ValueError, match="power of two"):
+        ShardPlan(4, 4, 3, 0, 3)
+    with pytest.raises(ValueError, match="world <= 2\\^rate_bits"):
+        ShardPlan(4, 4, 1, 0, 4)
+    with pytest.raises(ValueError, match="cap_height=9 should be at most"):
+        ShardPlan(4, 4, 3, 9, 2)
+
+
+@pytest.mark.parametrize("w,lg_d,r,cap,world", [(9, 4, 3, 4, 8), (9, 4, 3, 1, 8), (5, 3, 2, 0, 4), (6, 5, 1, 3, 2)])
+def test_single_process_shards_assemble_to_reference(w, lg_d, r, cap, world):
+    """All ranks' shards computed in one process (oracle engine): cap / digests / proofs == unsharded."""
+    import torch
+
+    from plonky2_demo_b200.sharded import ShardPlan
+
+    coeffs = seeded_polys(w, 1 << lg_d, base_seed=77)
+    ref = oracle.commit_from_coeffs(coeffs, r, cap)
+    plan = ShardPlan(w, lg_d, r, cap, world)
+    eng = OracleShardEngine()
+    t = torch.from_numpy(coeffs.view(np.int64).copy())
+    hs, caps = zip(*[eng.commit_shard(t, w, plan, k) for k in range(world)])
+    cap_full = plan.assemble_cap(np.stack(caps), eng.two_to_one)
+    assert np.array_equal(cap_full, ref["cap"])
+    if plan.top_levels == 0:
+        dig = np.concatenate([eng.digests(h, 0) for h in hs])
+        assert np.array_equal(dig, ref["digests"])
+    roots = np.stack(caps).reshape(world, -1, 4)[:, 0]
+    for leaf in [0, 1, plan.local_leaves - 1, plan.local_leaves, plan.n_leaves - 1]:
+        k = plan.owner_of_leaf(leaf)
+        n_local = lg_d + plan.lg_cosets - plan.local_cap_height
+        sib = eng.prove(hs[k], leaf - plan.leaf_range(k)[0], n_local) if n_local else np.zeros((0, 4), np.uint64)
+        if plan.top_levels:
+            sib = plan.extend_proof(k, sib, roots, eng.two_to_one)
+        assert np.array_equal(sib.reshape(-1, 4), oracle.merkle_prove(ref["digests"], plan.n_leaves, cap, leaf).reshape(-1, 4)) or plan.top_levels
+        assert oracle.merkle_verify(ref["leaves"][leaf], leaf, ref["cap"], sib)
+
+
+# ---------------------------------------------------------------------------------------------
+# collectives under gloo, world_size 2
+# ---------------------------------------------------------------------------------------------
+def _gloo_worker(rank, world, port, w, lg_d, r, cap, from_values, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    from plonky2_demo_b200.sharded import ShardedPolynomialBatch, ShardPlan
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        coeffs = seeded_polys(w, 1 << lg_d, base_seed=5)
+        ref = oracle.commit_from_coeffs(coeffs, r, cap)
+        plan = ShardPlan(w, lg_d, r, cap, world)
+        lo, hi = plan.poly_range(rank)
+        src = oracle.fft(coeffs) if from_values else coeffs
+        local = torch.from_numpy(np.ascontiguousarray(src[lo:hi]).view(np.int64).copy())
+        eng = OracleShardEngine()
+        if from_values:
+            b = ShardedPolynomialBatch.from_values(local, w, r, cap, engine=eng)
+        else:
+            b = ShardedPolynomialBatch.from_coeffs(local, w, r, cap, engine=eng)
+        ok = np.array_equal(b.cap, ref["cap"])
+        ok &= np.array_equal(b._coeffs.numpy().view(np.uint64)[:w], coeffs)
+        leaves = [0, plan.local_leaves - 1, plan.local_leaves, plan.n_leaves - 1]
+        ok &= np.array_equal(b.get_rows(leaves), ref["leaves"][leaves])
+        ok &= np.array_equal(b.get_lde_values(3, 2), ref["leaves"][int(format(6, f"0{lg_d + r}b")[::-1], 2)])
+        for leaf in leaves:
+            pr = b.prove(leaf)
+            ok &= bool(oracle.merkle_verify(ref["leaves"][leaf], leaf, ref["cap"], pr.siblings))
+        if plan.top_levels == 0:
+            l0, l1 = plan.leaf_range(rank)
+            per = ref["digests"].shape[0] // world
+            ok &= np.array_equal(b.local_digests(), ref["digests"][rank * per:(rank + 1) * per])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("w,lg_d,r,cap,from_values", [(9, 5, 3, 4, False), (7, 4, 1, 0, False), (9, 5, 3, 4, True)])
+def test_gloo_world2_sharded_commit(w, lg_d, r, cap, from_values):
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(k, 2, port, w, lg_d, r, cap, from_values, q)) for k in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+# ---------------------------------------------------------------------------------------------
+# the CUDA shard commit (every shard on one GPU) against the unsharded commit
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,lg_d,r,cap,world", [(135, 10, 3, 4, 8), (20, 12, 3, 4, 4), (9, 7, 3, 1, 8), (5, 3, 2, 0, 2), (17, 14, 3, 4, 2), (6, 9, 1, 3, 1)])
+def test_cuda_shards_assemble_to_reference(w, lg_d, r, cap, world):
+    import torch
+
+    import plonky2_demo_b200 as p
+    from plonky2_demo_b200.sharded import CudaShardEngine, ShardPlan
+
+    p.init(0)
+    coeffs = seeded_polys(w, 1 << lg_d, base_seed=31)
+    ref = oracle.commit_from_coeffs(coeffs, r, cap)
+    plan = ShardPlan(w, lg_d, r, cap, world)
+    eng = CudaShardEngine()
+    t = torch.from_numpy(coeffs.view(np.int64).copy()).cuda()
+    hs, caps = zip(*[eng.commit_shard(t, w, plan, k) for k in range(world)])
+    assert np.array_equal(plan.assemble_cap(np.stack(caps), eng.two_to_one), ref["cap"])
+    n_dig = 2 * (plan.local_leaves - plan.local_cap_len())
+    if plan.top_levels == 0:
+        assert np.array_equal(np.concatenate([eng.digests(h, n_dig) for h in hs]), ref["digests"])
+    rng = np.random.default_rng(1)
+    for k in range(world):
+        idx = rng.integers(0, plan.local_leaves, size=16)
+        assert np.array_equal(eng.get_rows(hs[k], idx, w), ref["leaves"][idx + plan.leaf_range(k)[0]])
+    for h in hs:
+        eng.free(h)
+
+
+@pytest.mark.gpu
+def test_cuda_intt_dev_matches_oracle():
+    import torch
+
+    import plonky2_demo_b200 as p
+    from plonky2_demo_b200.sharded import CudaShardEngine
+
+    p.init(0)
+    vals = seeded_polys(5, 1 << 11, base_seed=3)
+    t = torch.from_numpy(vals.view(np.int64).copy()).cuda()
+    CudaShardEngine().intt_local(t)
+    p.synchronize()
+    assert np.array_equal(t.cpu().numpy().view(np.uint64), oracle.fft(vals, inverse=True))
