@@ -399,6 +399,10 @@ def run_ours(a):
 
 
 if __name__ == "__main__":
+    # the driver reads ONE JSON line from stdout: keep library chatter (e.g. NCCL's version banner) off it
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real_stdout, "w")
     args = parse()
     if args.impl == "reference":
         run_reference(args)

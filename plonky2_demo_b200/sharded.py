@@ -255,6 +255,7 @@ class ShardedPolynomialBatch:
         if self._h is not None:
             self.engine.free(self._h)
             self._h = None
+        self._coeffs = None   # release the gathered coefficient matrix as well
 
     def __del__(self):
         try:
