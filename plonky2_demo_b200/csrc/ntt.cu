@@ -179,7 +179,12 @@ struct PassArgs {
     int last;                  // last pass: outputs leave the engine => canonical
 };
 
-__device__ __forceinline__ uint32_t sw(uint32_t E) { return E ^ ((E >> 5) & 31u); }
+// Shared-memory swizzle of a tile coordinate.  XOR-linear: sw(a ^ b) = sw(a) ^ sw(b), so an access at
+// (thread base | compile-time field value) costs one LOP3 with an immediate: sw(base) ^ sw(const).
+__host__ __device__ constexpr uint32_t sw(uint32_t E) { return E ^ ((E >> 5) & 31u); }
+__device__ __forceinline__ uint64_t& tile_at(uint64_t* tile, uint32_t base_bytes, uint32_t c) {
+    return *reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(tile) + (base_bytes ^ (sw(c) << 3)));
+}
 
 // K stages on 32 registers; stage s pairs (j, j+16) with twiddle twp[s*16*STRIDE + j*STRIDE] and
 // rotates the register index left by one bit.
@@ -199,7 +204,7 @@ __device__ __forceinline__ void run_stages(uint64_t (&x)[32], const uint64_t* tw
     }
 }
 
-template <int K1, int K2>
+template <int K1, int K2, int LCL>
 __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassArgs a) {
     constexpr int NB = K1 + K2;
     constexpr int LC = NTT_TILE_LOG - NB;
@@ -210,8 +215,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassArgs a) {
     uint64_t* tw2 = tw1 + 16 * K1;         // [K2][16][32]
     uint64_t* gam = tw2 + 512 * K2;        // [NB]
     const uint32_t tid = threadIdx.x;
-    const uint32_t lcl = a.lcl;
-    const uint32_t PB = LC - lcl;          // polynomial bits of the tile coordinate
+    constexpr uint32_t lcl = LCL;          // log2(columns taken from the low index bits); compile time so that
+    constexpr uint32_t PB = LC - lcl;      // every tile / shared-memory address folds to base + immediate
 
     // ---- which prefix / which column groups ----
     const uint32_t gbits = a.r + a.s0;
@@ -242,19 +247,21 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassArgs a) {
 
     // ---- per-thread coordinates (same for every tile) ----
     // round 1: field = rho bits [NB-1 .. K2]; thread bits = [pcol_low | rho_lo (K2) | lcol]
-    const uint32_t lmask = (1u << lcl) - 1;
+    constexpr uint32_t lmask = (1u << lcl) - 1;
     const uint32_t lcol1 = tid & lmask;
     const uint32_t rlo1 = (tid >> lcl) & ((1u << K2) - 1);
     const uint32_t pl1 = tid >> (lcl + K2);
-    const uint32_t xsh1 = PB - (5 - K1);                   // extras -> top polynomial bits
+    constexpr uint32_t xsh1 = PB - (5 - K1);               // extras -> top polynomial bits
     const uint32_t E1 = (pl1 << (NB + lcl)) | (rlo1 << lcl) | lcol1;
-    const uint32_t p1 = lcl + K2;
+    const uint32_t sb1 = sw(E1) << 3;                       // byte offset of the thread's round-1 base
+    constexpr uint32_t p1 = lcl + K2;
     // round 2: field = rho bits [K2-1 .. 0]; thread bits = [pcol_low | rho_hi (K1) | lcol]
     const uint32_t rhi2 = (tid >> lcl) & ((1u << K1) - 1);
     const uint32_t pl2 = tid >> (lcl + K1);
-    const uint32_t xsh2 = PB - (5 - K2);
+    constexpr uint32_t xsh2 = K2 > 0 ? PB - (5 - K2) : 0;
     const uint32_t E2 = (pl2 << (NB + lcl)) | (rhi2 << (K2 + lcl)) | (tid & lmask);
-    const bool staged_out = K2 > 0 && lcl < 3;
+    const uint32_t sb2 = sw(E2) << 3;
+    constexpr bool staged_out = K2 > 0 && lcl < 3;
 
     for (uint32_t ti = 0; ti < a.tiles_per_cta; ti++) {
         const uint32_t cg = cg0 + ti;
@@ -268,12 +275,15 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassArgs a) {
         uint64_t x[32];
         // ---- acquire round 1 straight from global memory ----
         {
+            const size_t row_stride = (size_t)1 << (K2 + a.L);   // elements between consecutive field values
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const uint32_t av = j >> (5 - K1), xv = j & ((1 << (5 - K1)) - 1);
-                const uint32_t poly = poly_base + pl1 + (xv << xsh1);
-                const size_t idx = (size_t)poly * a.in_poly_stride + ((size_t)((av << K2) | rlo1) << a.L) + lcol1;
-                x[j] = poly < a.n_polys ? in_t[idx] : 0;
+            for (int xv = 0; xv < (1 << (5 - K1)); xv++) {
+                // polynomials past the end of the batch read the last one's data: their results are never stored
+                uint32_t poly = poly_base + pl1 + (xv << xsh1);
+                poly = poly < a.n_polys ? poly : a.n_polys - 1;
+                const uint64_t* pp = in_t + (size_t)poly * a.in_poly_stride + ((size_t)rlo1 << a.L) + lcol1;
+#pragma unroll
+                for (int av = 0; av < (1 << K1); av++, pp += row_stride) x[(av << (5 - K1)) | xv] = *pp;
             }
         }
         run_stages<1>(x, tw1, K1);
@@ -282,13 +292,13 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassArgs a) {
 #pragma unroll
             for (int m = 0; m < 32; m++) {
                 const uint32_t av = m & ((1 << K1) - 1), xv = m >> K1;
-                tile[sw(E1 + (av << p1) + (xv << (8 + K1)))] = x[m];
+                tile_at(tile, sb1, (av << p1) | (xv << (8 + K1))) = x[m];
             }
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < 32; j++) {
                 const uint32_t av = j >> (5 - K2), xv = j & ((1 << (5 - K2)) - 1);
-                x[j] = tile[sw(E2 + (av << lcl) + (xv << (8 + K2)))];
+                x[j] = tile_at(tile, sb2, (av << lcl) | (xv << (8 + K2)));
             }
             run_stages<32>(x, tw2 + rhi2, K2);
         }
@@ -304,24 +314,29 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassArgs a) {
 #pragma unroll
             for (int m = 0; m < 32; m++) {
                 const uint32_t av = m & ((1 << KL) - 1), xv = m >> KL;
-                tile[sw(E2 + (av << lcl) + (xv << (8 + KL)))] = x[m];
+                tile_at(tile, sb2, (av << lcl) | (xv << (8 + KL))) = x[m];
             }
             __syncthreads();
 #pragma unroll 8
             for (uint32_t e = tid; e < TILE; e += NTT_THREADS) {
                 const uint32_t poly = poly_base + (e >> (NB + lcl));
-                // staged mode implies L == lcl: [rho | lcol] is contiguous in memory
-                if (poly < a.n_polys) out_t[(size_t)poly * a.out_poly_stride + (e & ((1u << (NB + lcl)) - 1))] = tile[sw(e)];
+                // staged mode is used by last passes (L == lcl == 0: rho is contiguous in memory)
+                const uint32_t within = e & ((1u << (NB + lcl)) - 1);
+                if (poly < a.n_polys)
+                    out_t[(size_t)poly * a.out_poly_stride + ((size_t)(within >> lcl) << a.L) + (within & lmask)] = tile[sw(e)];
             }
         } else {
             const uint32_t rbase = K2 > 0 ? (rhi2 << K2) : rlo1;   // K2 == 0: round-1 coordinates (rlo1 == 0)
             const uint32_t plx = K2 > 0 ? pl2 : pl1, xshx = K2 > 0 ? xsh2 : xsh1, lc_ = K2 > 0 ? (tid & lmask) : lcol1;
+            const size_t row_stride = (size_t)1 << a.L;
 #pragma unroll
-            for (int m = 0; m < 32; m++) {
-                const uint32_t av = m & ((1 << KL) - 1), xv = m >> KL;
+            for (int xv = 0; xv < (1 << (5 - KL)); xv++) {
                 const uint32_t poly = poly_base + plx + (xv << xshx);
-                const size_t idx = (size_t)poly * a.out_poly_stride + ((size_t)(rbase | av) << a.L) + lc_;
-                if (poly < a.n_polys) out_t[idx] = x[m];
+                uint64_t* pp = out_t + (size_t)poly * a.out_poly_stride + ((size_t)rbase << a.L) + lc_;
+                if (poly < a.n_polys) {
+#pragma unroll
+                    for (int av = 0; av < (1 << KL); av++, pp += row_stride) *pp = x[(xv << KL) | av];
+                }
             }
         }
         __syncthreads();   // the tile buffer is rewritten by the next iteration
@@ -337,18 +352,26 @@ __global__ void k_broadcast_const(const uint64_t* in, size_t in_stride, uint64_t
     out[j * out_stride + k] = gl::canon(gl::mul(gl::canon(in[j * in_stride]), scale));
 }
 
-typedef void (*pass_kernel_t)(const PassArgs);
-template <int K1, int K2>
+// columns from the low index bits when a pass has stages below it: as many as fit the tile (13 - nb bits) while a
+// thread's round-2 twiddle row still depends on its thread index only (lcl + K1 <= 8)
+constexpr int lcl_max(int k1, int k2) { return (13 - k1 - k2) < (8 - k1) ? (13 - k1 - k2) : (8 - k1); }
+
+template <int K1, int K2, int LCL>
 static cudaError_t launch_pass(const PassArgs& a, unsigned grid, cudaStream_t st) {
     constexpr size_t smem = ((size_t)(1u << NTT_TILE_LOG) + 16 * K1 + 512 * K2 + 16) * sizeof(uint64_t);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_ntt_pass<K1, K2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_ntt_pass<K1, K2, LCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k_ntt_pass<K1, K2><<<grid, NTT_THREADS, smem, st>>>(a);
+    k_ntt_pass<K1, K2, LCL><<<grid, NTT_THREADS, smem, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int K1, int K2>
+static cudaError_t launch_pass_lcl(const PassArgs& a, unsigned grid, cudaStream_t st) {
+    return a.lcl ? launch_pass<K1, K2, lcl_max(K1, K2)>(a, grid, st) : launch_pass<K1, K2, 0>(a, grid, st);
 }
 
 static cudaError_t run_passes(const NttPlan* plan, const uint64_t* in, size_t in_stride, uint64_t* out,
@@ -382,8 +405,10 @@ static cudaError_t run_passes(const NttPlan* plan, const uint64_t* in, size_t in
         a.c0 = coset_first;
         // columns from the low index bits: at most L, at most lc, and few enough that a thread's
         // round-2 twiddle row depends on its thread index only (lcl + k1 <= 8)
-        unsigned lcl = ps.L < lc ? ps.L : lc;
-        if (lcl > 8 - k1) lcl = 8 - k1;
+        // L is 0 (last pass) or the stage count of the later passes (>= 5 for every plan split_stages makes); the
+        // kernels are instantiated for lcl = 0 and lcl = lcl_max only
+        unsigned lclm = lc < 8 - k1 ? lc : 8 - k1;
+        unsigned lcl = ps.L >= lclm ? lclm : 0;
         a.lcl = lcl;
         a.lgroups = 1u << (ps.L - lcl);
         uint32_t polys_per_tile = 1u << (lc - lcl);
@@ -405,16 +430,16 @@ static cudaError_t run_passes(const NttPlan* plan, const uint64_t* in, size_t in
         unsigned grid = (unsigned)n_blocks;
         cudaError_t e;
         switch (nb) {
-            case 1: e = launch_pass<1, 0>(a, grid, st); break;
-            case 2: e = launch_pass<2, 0>(a, grid, st); break;
-            case 3: e = launch_pass<3, 0>(a, grid, st); break;
-            case 4: e = launch_pass<4, 0>(a, grid, st); break;
-            case 5: e = launch_pass<5, 0>(a, grid, st); break;
-            case 6: e = launch_pass<3, 3>(a, grid, st); break;
-            case 7: e = launch_pass<4, 3>(a, grid, st); break;
-            case 8: e = launch_pass<4, 4>(a, grid, st); break;
-            case 9: e = launch_pass<5, 4>(a, grid, st); break;
-            case 10: e = launch_pass<5, 5>(a, grid, st); break;
+            case 1: e = launch_pass_lcl<1, 0>(a, grid, st); break;
+            case 2: e = launch_pass_lcl<2, 0>(a, grid, st); break;
+            case 3: e = launch_pass_lcl<3, 0>(a, grid, st); break;
+            case 4: e = launch_pass_lcl<4, 0>(a, grid, st); break;
+            case 5: e = launch_pass_lcl<5, 0>(a, grid, st); break;
+            case 6: e = launch_pass_lcl<3, 3>(a, grid, st); break;
+            case 7: e = launch_pass_lcl<4, 3>(a, grid, st); break;
+            case 8: e = launch_pass_lcl<4, 4>(a, grid, st); break;
+            case 9: e = launch_pass_lcl<5, 4>(a, grid, st); break;
+            case 10: e = launch_pass_lcl<5, 5>(a, grid, st); break;
             default: e = cudaErrorInvalidConfiguration;
         }
         if (e != cudaSuccess) return e;
