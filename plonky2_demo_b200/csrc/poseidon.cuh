@@ -183,6 +183,97 @@ __device__ __forceinline__ void mds_layer_fp64(uint64_t (&s)[12], const uint64_t
     for (int r = 0; r < 12; r++) s[r] = gl::fold_halves_biased(l0[r], l1[r], h0[r], h1[r]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Partial rounds with lanes 1..11 RESIDENT in the FP64 network's domain.
+//
+// In the 22 partial rounds only lane 0 passes the S-box, so only lane 0 has to exist as a 64-bit integer.
+// Lanes 1..11 stay as pairs of exact doubles (lo, hi), value = lo + hi * 2^32 (mod p), and go from one
+// round's network output straight into the next round's network input: no 96-bit fold, no int<->double
+// re-biasing for 11 of the 12 lanes.  Magnitudes grow by the MDS row sum (264 < 2^8.05) per round, and the
+// network's widest intermediate is bounded by 2^8.5 x its inputs (L1 norms checked symbolically in
+// tests/test_mds_network_bounds.py), so TWO rounds fit the 53-bit significand:
+//     normalised inputs < 2^33.01 -> round A outputs < 2^41.1 -> round B intermediates < 2^49.7, outputs < 2^49.2.
+// After round B the lanes are renormalised in 8 FP64 operations each (floor by the 2^52 trick with
+// round-down FMAs, 2^64 = 2^32 - 1 folded back, plus one multiple of p so that both halves stay positive):
+//     lo'' = lo - (l1-1) 2^32 - (h1-1)                 in [2^32 - 2^18, 2^33]
+//     hi'' = hi - (h1-1)(2^32 - 1) + (l1-1)            in [2^32 - 2, 2^33 + 2^19),      l1 = lo >> 32, h1 = hi >> 32
+//     lo'' + hi'' 2^32 = lo + hi 2^32 + p - h1 (2^64 - 2^32 + 1)  ==  lo + hi 2^32   (mod p).
+// The scalar round constant is added to lane 0 right after its S-box (poseidon.rs:584-596 does the same in
+// the "fast" form), so the network carries no per-lane constants in these rounds.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double u32_as_double(uint32_t x) { return __hiloint2double(0x43300000, (int)x) - TWO52; }
+
+// y = circ-correlation(s) + 8*s0*e0 on exact doubles (no constants)
+__device__ __forceinline__ void mds_net_d(const double (&s)[12], double (&y)[12]) {
+    double A[3], B[3], P[3], Q[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        double u = s[j] + s[j + 6], v = s[j + 3] + s[j + 9];
+        A[j] = u + v;
+        B[j] = u - v;
+        P[j] = s[j] - s[j + 6];
+        Q[j] = s[j + 3] - s[j + 9];
+    }
+    double t = A[0] + A[1] + A[2];
+    double Ya[3] = {t + A[2], t + A[0], t + A[1]};  // times 16, applied below
+    double Yb[3] = {fma(B[1], -2.0, fma(B[2], 8.0, -B[0])),
+                    fma(B[2], -2.0, fma(B[0], -8.0, -B[1])),
+                    fma(B[1], -8.0, fma(B[0], 2.0, -B[2]))};
+    double re[3], im[3];
+    re[0] = fma(Q[2], 4.0, fma(Q[1], -16.0, fma(P[0], 2.0, -Q[0]) + P[1]) + P[2]);
+    im[0] = fma(P[2], -4.0, fma(P[1], 16.0, fma(Q[0], 2.0, P[0]) + Q[1]) + Q[2]);
+    re[1] = fma(Q[2], -16.0, fma(P[1], 2.0, fma(P[0], -4.0, Q[0]) - Q[1]) + P[2]);
+    im[1] = fma(P[2], 16.0, fma(Q[1], 2.0, fma(Q[0], -4.0, -P[0]) + P[1]) + Q[2]);
+    re[2] = fma(P[2], 2.0, fma(P[1], -4.0, fma(P[0], 16.0, Q[0]) + Q[1]) - Q[2]);
+    im[2] = fma(Q[2], 2.0, fma(Q[1], -4.0, fma(Q[0], 16.0, -P[0]) - P[1]) + P[2]);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        double e1 = fma(Ya[j], 16.0, Yb[j]), e2 = fma(Ya[j], 16.0, -Yb[j]);
+        y[j] = e1 + re[j];
+        y[j + 3] = e2 + im[j];
+        y[j + 6] = e1 - re[j];
+        y[j + 9] = e2 - im[j];
+    }
+    y[0] = fma(s[0], 8.0, y[0]);  // MDS_MATRIX_DIAG[0] = 8
+}
+
+// (lo, hi) < 2^52, positive  ->  equivalent pair with both halves in [2^32 - 2^18, 2^33 + 2^19)
+__device__ __forceinline__ void renorm_d(double& lo, double& hi) {
+    const double M1 = TWO52 + 1.0, INV32 = 1.0 / 4294967296.0;
+    double l1m = __fma_rd(lo, INV32, TWO52) - M1;   // (lo >> 32) - 1
+    double h1m = __fma_rd(hi, INV32, TWO52) - M1;   // (hi >> 32) - 1
+    double lo2 = fma(l1m, -4294967296.0, lo) - h1m;
+    double hi2 = fma(h1m, -4294967295.0, hi) + l1m;
+    lo = lo2;
+    hi = hi2;
+}
+
+// lane value (lo + hi 2^32, both < 2^52 and >= 0) as a loose u64
+__device__ __forceinline__ uint64_t fold_d(double lo, double hi) {
+    double bl = lo + TWO52, bh = hi + TWO52;
+    return gl::fold_halves_biased((uint32_t)__double2loint(bl), (uint32_t)__double2hiint(bl),
+                                  (uint32_t)__double2loint(bh), (uint32_t)__double2hiint(bh));
+}
+
+// one partial round: lane 0 = x0 (integer), lanes 1..11 = (dl, dh); yl/yh receive M * state
+__device__ __forceinline__ void partial_round_d(uint64_t& x0, double (&dl)[12], double (&dh)[12], uint64_t rc) {
+    x0 = gl::add_lc(sbox7(x0), rc);
+    dl[0] = u32_as_double((uint32_t)x0);
+    dh[0] = u32_as_double((uint32_t)(x0 >> 32));
+    double yl[12], yh[12];
+    mds_net_d(dl, yl);
+    mds_net_d(dh, yh);
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        dl[i] = yl[i];
+        dh[i] = yh[i];
+    }
+}
+
+#ifndef PCS_PARTIAL_FP64
+#define PCS_PARTIAL_FP64 1
+#endif
+
 // The permutation.  Input lanes: any u64 (loose); output lanes: canonical.
 //
 // ONE round loop for all 30 rounds (the body is ~22 KB of SASS and must stay resident in the SM's
@@ -191,30 +282,63 @@ __device__ __forceinline__ void mds_layer_fp64(uint64_t (&s)[12], const uint64_t
 // covers all lanes in the 8 full rounds and lane 0 only in the 22 partial rounds (warp-uniform
 // branch) and ROUND_ADD[r] is the constant needed by the NEXT s-box layer moved behind the linear
 // layer (tests/golden/make_golden.py:round_addends); it is absorbed by 3-input adds of the network.
+__device__ __forceinline__ void full_round(uint64_t (&s)[12], int r) {
+    using namespace pconst;
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
+#if PCS_MDS_FP64
+    mds_layer_fp64(s, &ROUND_ADD_D[24 * r]);
+#else
+    mds_layer<1>(s, &ROUND_ADD[12 * r]);
+#endif
+}
+
 __device__ __forceinline__ void poseidon12(uint64_t (&s)[12]) {
     using namespace pconst;
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl::add_lc(s[i], RC[i]);
+#if PCS_PARTIAL_FP64 && PCS_MDS_FP64
+    // rounds 0..3 (full), 4..25 (partial, FP64-resident lanes), 26..29 (full): the two full-round groups share
+    // ONE loop body (phase 0 and phase 1) so that the code stays small enough for the instruction cache
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) full_round(s, 26 * phase + r);
+        if (phase == 0) {
+            uint64_t x0 = s[0];
+            double dl[12], dh[12];
+#pragma unroll
+            for (int i = 1; i < 12; i++) {
+                dl[i] = u32_as_double((uint32_t)s[i]);
+                dh[i] = u32_as_double((uint32_t)(s[i] >> 32));
+            }
+#pragma unroll 1
+            for (int k = 0; k < 11; k++) {
+                partial_round_d(x0, dl, dh, PARTIAL_RC[2 * k]);        // inputs normalised
+                x0 = fold_d(dl[0], dh[0]);
+                partial_round_d(x0, dl, dh, PARTIAL_RC[2 * k + 1]);    // inputs up to 2^41
+                if (k < 10) {
+                    x0 = fold_d(dl[0], dh[0]);
+#pragma unroll
+                    for (int i = 1; i < 12; i++) renorm_d(dl[i], dh[i]);
+                }
+            }
+            // leave the FP64 domain: + RC[26] (the next full round's constants), all lanes back to integers
+            const double* rcd = reinterpret_cast<const double*>(&ROUND_ADD_D[24 * 25]);  // 2^52 + halves of RC[26..]
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                double bl = dl[i] + rcd[2 * i], bh = dh[i] + rcd[2 * i + 1];
+                s[i] = gl::fold_halves_biased((uint32_t)__double2loint(bl), (uint32_t)__double2hiint(bl),
+                                              (uint32_t)__double2loint(bh), (uint32_t)__double2hiint(bh));
+            }
+        }
+    }
+#else
 #pragma unroll 1
     for (int r = 0; r < 30; r++) {
         if (r < 4 || r >= 26) {
-#if PCS_SBOX_GROUP == 12
 #pragma unroll
             for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
-#else
-            // S-box layer as a loop over groups of lanes; the state is rotated by one group after
-            // each pass (register moves), so the loop body is 1/(12/GROUP) of the code.
-#pragma unroll 1
-            for (int g = 0; g < 12 / PCS_SBOX_GROUP; g++) {
-                uint64_t t[PCS_SBOX_GROUP];
-#pragma unroll
-                for (int i = 0; i < PCS_SBOX_GROUP; i++) t[i] = sbox7(s[i]);
-#pragma unroll
-                for (int i = 0; i < 12 - PCS_SBOX_GROUP; i++) s[i] = s[i + PCS_SBOX_GROUP];
-#pragma unroll
-                for (int i = 0; i < PCS_SBOX_GROUP; i++) s[12 - PCS_SBOX_GROUP + i] = t[i];
-            }
-#endif
         } else {
             s[0] = sbox7(s[0]);
         }
@@ -224,6 +348,7 @@ __device__ __forceinline__ void poseidon12(uint64_t (&s)[12]) {
         mds_layer<1>(s, &ROUND_ADD[12 * r]);
 #endif
     }
+#endif
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl::canon(s[i]);
 }
