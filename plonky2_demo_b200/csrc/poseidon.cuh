@@ -203,15 +203,18 @@ __device__ __forceinline__ void mds_layer_fp64(uint64_t (&s)[12], const uint64_t
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double u32_as_double(uint32_t x) { return __hiloint2double(0x43300000, (int)x) - TWO52; }
 
-// y = circ-correlation(s) + 8*s0*e0 on exact doubles (no constants)
+// y = circ-correlation(s) + 8*s0*e0 on exact doubles (no constants).  ZERO0: lane 0 is taken as 0 (its
+// contribution is added afterwards, see partial_round_d).
+template <bool ZERO0>
 __device__ __forceinline__ void mds_net_d(const double (&s)[12], double (&y)[12]) {
     double A[3], B[3], P[3], Q[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        double u = s[j] + s[j + 6], v = s[j + 3] + s[j + 9];
+        const bool z = ZERO0 && j == 0;
+        double u = z ? s[6] : s[j] + s[j + 6], v = s[j + 3] + s[j + 9];
         A[j] = u + v;
         B[j] = u - v;
-        P[j] = s[j] - s[j + 6];
+        P[j] = z ? -s[6] : s[j] - s[j + 6];
         Q[j] = s[j + 3] - s[j + 9];
     }
     double t = A[0] + A[1] + A[2];
@@ -234,7 +237,7 @@ __device__ __forceinline__ void mds_net_d(const double (&s)[12], double (&y)[12]
         y[j + 6] = e1 - re[j];
         y[j + 9] = e2 - im[j];
     }
-    y[0] = fma(s[0], 8.0, y[0]);  // MDS_MATRIX_DIAG[0] = 8
+    if (!ZERO0) y[0] = fma(s[0], 8.0, y[0]);  // MDS_MATRIX_DIAG[0] = 8
 }
 
 // (lo, hi) < 2^52, positive  ->  equivalent pair with both halves in [2^32 - 2^18, 2^33 + 2^19)
@@ -255,19 +258,39 @@ __device__ __forceinline__ uint64_t fold_d(double lo, double hi) {
                                   (uint32_t)__double2loint(bh), (uint32_t)__double2hiint(bh));
 }
 
-// one partial round: lane 0 = x0 (integer), lanes 1..11 = (dl, dh); yl/yh receive M * state
+// One partial round: lane 0 = x0 (integer), lanes 1..11 = (dl, dh); (dl, dh) receive M * state.
+// M s = M (0, s1..s11) + x0' * M[:,0]: the bulk network does not depend on this round's S-box, so the FP64
+// work of lanes 1..11 and the (serial, latency-bound) integer S-box chain of lane 0 are independent
+// instruction streams that the scheduler interleaves; lane 0 then enters through 12 FMAs per half.
+#ifndef PCS_PARTIAL_SPLIT
+#define PCS_PARTIAL_SPLIT 0   // measured: 203.6 vs 199.2 clk per permutation with the split (the extra 24 FMAs cost more than the ILP gains)
+#endif
 __device__ __forceinline__ void partial_round_d(uint64_t& x0, double (&dl)[12], double (&dh)[12], uint64_t rc) {
+    double yl[12], yh[12];
+#if PCS_PARTIAL_SPLIT
+    mds_net_d<true>(dl, yl);
+    mds_net_d<true>(dh, yh);
+    x0 = gl::add_lc(sbox7(x0), rc);
+    const double al = u32_as_double((uint32_t)x0), ah = u32_as_double((uint32_t)(x0 >> 32));
+    // M[i][0] = MDS_MATRIX_CIRC[(12 - i) % 12] (+ MDS_MATRIX_DIAG[0] for i = 0)   poseidon_goldilocks.rs:24-25
+    constexpr double COL0[12] = {25.0, 20.0, 34.0, 18.0, 39.0, 13.0, 13.0, 28.0, 2.0, 16.0, 41.0, 15.0};
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        dl[i] = fma(al, COL0[i], yl[i]);
+        dh[i] = fma(ah, COL0[i], yh[i]);
+    }
+#else
     x0 = gl::add_lc(sbox7(x0), rc);
     dl[0] = u32_as_double((uint32_t)x0);
     dh[0] = u32_as_double((uint32_t)(x0 >> 32));
-    double yl[12], yh[12];
-    mds_net_d(dl, yl);
-    mds_net_d(dh, yh);
+    mds_net_d<false>(dl, yl);
+    mds_net_d<false>(dh, yh);
 #pragma unroll
     for (int i = 0; i < 12; i++) {
         dl[i] = yl[i];
         dh[i] = yh[i];
     }
+#endif
 }
 
 #ifndef PCS_PARTIAL_FP64

@@ -1,0 +1,113 @@
+#!/usr/bin/env python3
+"""BASELINE.json configs[4]: one commitment of 135 polys x 2^24, rate_bits 3 (2^27 leaves, 145 GB of LDE rows)
+sharded over the GPUs of one box.  Run under torchrun, one rank per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 \
+        tools/large_commit_check.py [--lg-d 24] [--width 135]
+
+The LDE rows never leave the GPUs.  Parity at this size (the CPU oracle cannot hold 145 GB) is checked the way
+SURVEY 8d prescribes: sampled leaves are fetched with their Merkle paths and (i) the path is verified against the
+gathered cap by the CPU oracle, (ii) the row is compared with a direct CPU evaluation of the polynomials at that
+leaf's domain point g * w_N^{brev(leaf)} (fri/verifier.rs:185-186 pins this order)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lg-d", type=int, default=24)
+    ap.add_argument("--width", type=int, default=135)
+    ap.add_argument("--rate-bits", type=int, default=3)
+    ap.add_argument("--cap-height", type=int, default=4)
+    ap.add_argument("--samples", type=int, default=3)
+    ap.add_argument("--eval-polys", type=int, default=4, help="polynomials evaluated directly on the CPU per sampled leaf")
+    a = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+
+    import oracle
+    import plonky2_demo_b200 as pcs
+    from helpers import P, brev, splitmix64_stream
+    from plonky2_demo_b200.sharded import ShardedPolynomialBatch, ShardPlan
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    pcs.init(local, stream.cuda_stream)
+
+    w, lg_d, r, cap_h = a.width, a.lg_d, a.rate_bits, a.cap_height
+    d = 1 << lg_d
+    plan = ShardPlan(w, lg_d, r, cap_h, world)
+    lo, hi = plan.poly_range(rank)
+    t0 = time.perf_counter()
+    host = np.empty((hi - lo, d), dtype=np.uint64)
+    for j in range(hi - lo):
+        host[j] = splitmix64_stream(0x5EED0000 + lo + j, d)
+    local_coeffs = torch.from_numpy(host.view(np.int64)).to(dev)
+    gen_s = time.perf_counter() - t0
+
+    times = []
+    batch = None
+    for it in range(3):
+        if batch is not None:
+            batch.free()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        batch = ShardedPolynomialBatch.from_coeffs(local_coeffs, w, r, cap_h, partitioned=True)
+        e1.record(stream)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+
+    # ---- sampled parity ----
+    rng = np.random.default_rng(7)
+    n = plan.n_leaves
+    leaves = sorted(set([0, n - 1] + [int(x) for x in rng.integers(0, n, size=a.samples)]))
+    rows = batch.get_rows(leaves)
+    ok_paths, ok_rows = True, True
+    lg_n = lg_d + r
+    wN = oracle.primitive_root_of_unity(lg_n)
+    for k, leaf in enumerate(leaves):
+        proof = batch.prove(leaf)
+        if rank == 0:
+            ok_paths &= bool(oracle.merkle_verify(rows[k], leaf, batch.cap, proof.siblings))
+    # direct evaluation: each rank checks its own polynomials (first --eval-polys of its block) at every sampled point
+    for k, leaf in enumerate(leaves):
+        x = 7 * pow(wN, brev(leaf, lg_n), P) % P
+        for j in range(min(a.eval_polys, hi - lo)):
+            ok_rows &= int(rows[k][lo + j]) == oracle.poly_eval(host[j], x)
+    flag = torch.tensor([int(ok_rows)], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        elems = w * n
+        best = min(times)
+        print(json.dumps({
+            "config": f"large commit: {w} polys x 2^{lg_d}, rate_bits {r}, cap_height {cap_h}, sharded over {world} GPUs",
+            "ms": times, "best_ms": best, "elems_per_s": elems / (best * 1e-3), "lde_bytes": elems * 8,
+            "sampled_leaves": leaves, "merkle_paths_verify_against_cap": bool(ok_paths),
+            "rows_equal_direct_cpu_evaluation": bool(flag.item()), "polys_evaluated_per_rank": min(a.eval_polys, hi - lo),
+            "input_generation_s": gen_s, "cap0": [hex(int(v)) for v in batch.cap[0]]}))
+    batch.free()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
