@@ -77,6 +77,10 @@ PCS_API int pcs_two_to_one(const uint64_t* left /*[n][4]*/, const uint64_t* righ
 /* fft_with_options(.., None, ..) / ifft_with_options on w polynomials, natural order in and out.
  *                                                                 field/src/fft.rs:57-65, 72-95       */
 PCS_API int pcs_ntt(uint64_t* polys /*[w][n] in/out*/, size_t w, unsigned lg_n, int inverse);
+/* PolynomialValues::coset_ifft(shift) on w value vectors (natural order): coefficients of the polynomial whose
+ * evaluations on shift*<w_n> are given -- what compute_quotient_polys ends with (plonk/prover.rs:739-743).
+ *                                                                 field/src/polynomial/mod.rs:63-73   */
+PCS_API int pcs_coset_intt(uint64_t* values /*[w][n] in/out*/, size_t w, unsigned lg_n, uint64_t shift);
 /* The same transform in place on a DEVICE matrix [w][n] (natural order in and out), asynchronous on
  * pcs_stream(): the per-GPU IFFT of a polynomial-partitioned from_values.                */
 PCS_API int pcs_ntt_dev(uint64_t* polys_dev, size_t w, unsigned lg_n, int inverse);

@@ -26,6 +26,7 @@ SIGNATURES = {
     "pcs_hash_or_noop": (C.c_int, [u64p, sz, sz, u64p]),
     "pcs_two_to_one": (C.c_int, [u64p, u64p, sz, u64p]),
     "pcs_ntt": (C.c_int, [u64p, sz, C.c_uint, C.c_int]),
+    "pcs_coset_intt": (C.c_int, [u64p, sz, C.c_uint, C.c_uint64]),
     "pcs_ntt_dev": (C.c_int, [C.c_void_p, sz, C.c_uint, C.c_int]),
     "pcs_coset_lde": (C.c_int, [u64pp, sz, C.c_uint, C.c_uint, C.c_uint64, u64p, C.c_int]),
     "pcs_merkle_build": (C.c_int, [u64p, sz, sz, C.c_uint, u64p, u64p]),

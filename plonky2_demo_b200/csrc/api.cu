@@ -229,6 +229,38 @@ int pcs_ntt(uint64_t* polys, size_t w, unsigned lg_n, int inverse) {
     return PCS_OK;
 }
 
+static uint64_t host_inverse(uint64_t a) {  // a^(p-2) mod p
+    const uint64_t P = 0xFFFFFFFF00000001ULL;
+    unsigned __int128 acc = 1, b = a % P;
+    for (uint64_t e = P - 2; e; e >>= 1) {
+        if (e & 1) acc = acc * b % P;
+        b = b * b % P;
+    }
+    return (uint64_t)acc;
+}
+
+int pcs_coset_intt(uint64_t* values, size_t w, unsigned lg_n, uint64_t shift) {
+    PCS_NEED_INIT();
+    if (w == 0) return PCS_OK;
+    if (!values) return fail(PCS_ERR_ARG, "values is NULL");
+    if (lg_n > 32) return fail(PCS_ERR_TWO_ADICITY, "n_log <= TWO_ADICITY violated");
+    if (shift % 0xFFFFFFFF00000001ULL == 0) return fail(PCS_ERR_ARG, "shift must be non-zero");
+    cudaStream_t st = g_ctx.stream;
+    size_t n = (size_t)1 << lg_n;
+    NttPlan* plan = ntt_plan_get(lg_n, 0, true, 1, st);
+    if (!plan) return fail(PCS_ERR_ALLOC, "twiddle table allocation failed");
+    DevBuf a, b;
+    PCS_CUDA(a.alloc(w * n * 8, st));
+    PCS_CUDA(b.alloc(w * n * 8, st));
+    PCS_CUDA(cudaMemcpyAsync(a.p, values, w * n * 8, cudaMemcpyHostToDevice, st));
+    PCS_CUDA(ntt_lde(plan, a.u64(), n, b.u64(), n, w, st));
+    PCS_CUDA(launch_bitrev_permute(b.u64(), n, a.u64(), n, w, lg_n, st, ntt_plan_scale(plan)));
+    PCS_CUDA(launch_mul_powers(a.u64(), n, w, n, host_inverse(shift), st));   // c_i *= shift^-i  (mod.rs:68-72)
+    PCS_CUDA(cudaMemcpyAsync(values, a.p, w * n * 8, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
 int pcs_ntt_dev(uint64_t* polys_dev, size_t w, unsigned lg_n, int inverse) {
     PCS_NEED_INIT();
     if (w == 0) return PCS_OK;

@@ -81,5 +81,7 @@ cudaError_t launch_transpose(const uint64_t* in, size_t in_pitch, uint64_t* out,
 cudaError_t launch_gather_rows(const uint64_t* cols, size_t col_stride, uint32_t width, const uint64_t* idx,
                                size_t n_idx, uint64_t* out, cudaStream_t st);
 cudaError_t launch_canonicalize(uint64_t* data, size_t n, cudaStream_t st);
+// data[j][i] *= base^i for j < w, i < n (row stride `stride`)
+cudaError_t launch_mul_powers(uint64_t* data, size_t stride, size_t w, size_t n, uint64_t base, cudaStream_t st);
 
 }  // namespace pcs

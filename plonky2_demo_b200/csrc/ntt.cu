@@ -542,6 +542,23 @@ cudaError_t launch_gather_rows(const uint64_t* cols, size_t col_stride, uint32_t
     return cudaGetLastError();
 }
 
+// data[j][i] *= base^i   (coset_ifft: coefficients of P(shift x) -> coefficients of P, base = shift^-1)
+__global__ void k_mul_powers(uint64_t* data, size_t stride, size_t n, uint64_t base) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t* p = data + blockIdx.y * stride + i;
+    *p = gl::canon(gl::mul(*p, gl::pow(base, i)));
+}
+
+cudaError_t launch_mul_powers(uint64_t* data, size_t stride, size_t w, size_t n, uint64_t base, cudaStream_t st) {
+    if (w == 0 || n == 0) return cudaSuccess;
+    for (size_t j0 = 0; j0 < w; j0 += 65535) {
+        size_t wj = w - j0 < 65535 ? w - j0 : 65535;
+        k_mul_powers<<<dim3((unsigned)((n + 255) / 256), (unsigned)wj), 256, 0, st>>>(data + j0 * stride, stride, n, base);
+    }
+    return cudaGetLastError();
+}
+
 __global__ void k_canon(uint64_t* data, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) data[i] = gl::canon(data[i]);

@@ -104,6 +104,12 @@ class PolynomialValues:
     def ifft(self):
         return ifft_with_options(self, None, None)
 
+    def coset_ifft(self, shift):
+        """:63-73 coefficients from evaluations on shift*H (natural order)."""
+        v = _ffi.as_u64(self.values, copy=True).reshape(1, -1)
+        _ffi.check(_ffi.lib().pcs_coset_intt(_ffi.ptr(v), 1, log2_strict(v.shape[1]), int(shift) % GOLDILOCKS_ORDER))
+        return PolynomialCoeffs(v[0])
+
     def lde(self, rate_bits):
         """:79-82 evaluations of the same polynomial on the 2^rate_bits times larger subgroup."""
         return self.ifft().lde(rate_bits).coset_fft_with_options(1, rate_bits, None)

@@ -88,15 +88,31 @@ class ShardPlan:
 class CudaShardEngine:
     """Per-rank compute through the C ABI (no CPU path)."""
 
+    @staticmethod
+    def _order_after_torch():
+        """The collectives complete on torch's current stream, the engine enqueues on pcs_stream(): when the two
+        differ (the caller did not hand torch's stream to pcs_init) make the engine's work wait for torch's."""
+        import torch
+
+        cur = torch.cuda.current_stream()
+        if _ffi.lib().pcs_stream() != cur.cuda_stream:
+            cur.synchronize()
+
     def intt_local(self, values):
         """values: torch CUDA int64 tensor [w_local][d], transformed in place (values -> coefficients)."""
         if values.shape[0] == 0:
             return
+        self._order_after_torch()
         _ffi.check(_ffi.lib().pcs_ntt_dev(C.c_void_p(values.data_ptr()), values.shape[0], log2_strict(values.shape[1]), 1))
+        import torch
+
+        if _ffi.lib().pcs_stream() != torch.cuda.current_stream().cuda_stream:
+            _ffi.check(_ffi.lib().pcs_synchronize())   # the all-gather that follows runs on torch's stream
 
     def commit_shard(self, coeffs, w, plan, rank, keep_handle=True):
         """coeffs: torch CUDA int64 tensor [>= w][d] (contiguous).  Returns (handle, local cap [2^lch][4])."""
         L = _ffi.lib()
+        self._order_after_torch()
         d = coeffs.shape[1]
         ptrs = _ffi.dev_ptr_array(coeffs.data_ptr(), w, d)
         cap = np.empty((plan.local_cap_len(), 4), dtype=np.uint64)

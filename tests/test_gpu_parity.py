@@ -134,6 +134,23 @@ def test_coset_fft_and_lde_onto_coset(pcs):
     assert np.array_equal(lde1, oracle.coset_lde(c[None, :], 2, shift=1)[0])
 
 
+def test_coset_ifft_roundtrip_and_batch(pcs):
+    # polynomial/mod.rs:499-518 test_coset_ifft: coset_ifft(coset_fft(p)) == p; quotient-poly shape 16 x 2^12, shift 7
+    import ctypes as C
+
+    from plonky2_demo_b200 import _ffi
+
+    c = splitmix64_stream(9, 256)
+    for shift in (7, 3, P - 1):
+        vals = pcs.PolynomialCoeffs(c).coset_fft(shift)
+        assert np.array_equal(pcs.PolynomialValues(vals.values).coset_ifft(shift).coeffs, c)
+    coeffs = seeded_polys(16, 1 << 12, base_seed=44)
+    vals = oracle.coset_lde(coeffs, 0)            # evaluations on 7*H, natural order
+    got = vals.copy()
+    _ffi.check(_ffi.lib().pcs_coset_intt(_ffi.ptr(got), 16, 12, 7))
+    assert np.array_equal(got, coeffs)
+
+
 @pytest.mark.parametrize("lg_d,rate_bits,w", [(0, 3, 5), (1, 0, 4), (2, 2, 3), (3, 3, 135), (4, 0, 33), (5, 1, 7), (6, 3, 129), (7, 2, 70), (8, 1, 65), (9, 3, 20), (10, 3, 9), (11, 2, 16), (12, 4, 3), (13, 3, 17), (14, 1, 9), (15, 3, 6), (17, 2, 3), (18, 0, 2)])
 def test_coset_lde_layouts(pcs, lg_d, rate_bits, w):
     import ctypes as C
