@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--cpu-sample-lg-d", type=int, default=16, help="degree_log of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer"],
+                    help="N > 1: how coefficient blocks reach the other ranks (plonky2_demo_b200/sharded.py)")
     return ap.parse_args()
 
 
@@ -251,14 +253,14 @@ def run_ours(a):
 
     def commit_device():
         if world > 1:
-            return _Sharded(ShardedPolynomialBatch.from_coeffs(dev_coeffs, w, r, cap_h, partitioned=True))
+            return _Sharded(ShardedPolynomialBatch.from_coeffs(dev_coeffs, w, r, cap_h, partitioned=True, exchange=a.exchange))
         h = C.c_void_p()
         _ffi.check(L.pcs_commit_from_coeffs(dev_ptrs, w, lg_d, r, cap_h, None, 0, _ffi.PCS_DEVICE_PTRS, None, C.byref(h)))
         return h
 
     def commit_host():
         if world > 1:
-            b = ShardedPolynomialBatch.from_coeffs(host.to(dev, non_blocking=True), w, r, cap_h, partitioned=True)
+            b = ShardedPolynomialBatch.from_coeffs(host.to(dev, non_blocking=True), w, r, cap_h, partitioned=True, exchange=a.exchange)
             cap_host[:] = b.cap
             return _Sharded(b)
         h = C.c_void_p()
@@ -289,6 +291,7 @@ def run_ours(a):
     t_wall1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
     cap_dev = np.empty((1 << cap_h, 4), dtype=np.uint64)
+    prev_exchange = prev.b.exchange if world > 1 else "none"
     if world > 1:
         cap_dev[:] = prev.b.cap
     else:
@@ -374,8 +377,8 @@ def run_ours(a):
         "dtype": "u64 (Goldilocks field, integer)", "data": "synthetic",
         "config": {"workload": workload_name(a), "elems_per_step": elems, "input_coeff_elems_per_s": value / (1 << r),
                    "l2_policy": "inputs larger than L2 (1.13 GB coefficients, 9.06 GB LDE per step)",
-                   "parallelism": (f"one commitment sharded over {world} GPUs by coset block (contiguous leaf ranges): NCCL all-gather of "
-                                   f"coefficients, per-rank LDE + hashing, NCCL all-gather of the cap") if world > 1 else "single GPU"},
+                   "parallelism": (f"one commitment sharded over {world} GPUs by coset block (contiguous leaf ranges); coefficient exchange = "
+                                   f"{prev_exchange}; per-rank LDE + hashing; NCCL all-gather of the cap") if world > 1 else "single GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
         "roofline": roofline, "int_pipe": int_pipe, "kernels": kernels,
         "phase_ms": {"IFFT": phase[0], "FFT + blinding": phase[1], "transpose LDEs": phase[2], "leaf hashing": phase[3], "node levels": phase[4]},

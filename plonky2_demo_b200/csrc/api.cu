@@ -419,11 +419,19 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
     if (dev_ptrs)
         for (size_t j = 0; j < w; j++) contiguous_dev = contiguous_dev && polys[j] == polys[0] + j * d;
     const uint64_t* src = nullptr;   // [w][d] device input (values or coefficients)
+    DevBuf ptr_table;                // or: device table of the caller's w polynomial pointers, read in place
     uint64_t* staged = nullptr;
     constexpr size_t H2D_CHUNK = 16;  // polynomials per H2D chunk
     size_t n_chunks = 0;              // > 0: host inputs arrive chunk by chunk on the copy stream
     if (contiguous_dev && !from_values && !(flags & PCS_KEEP_COEFFS)) {
         src = polys[0];
+    } else if (dev_ptrs && !from_values && !(flags & PCS_KEEP_COEFFS) && lg_d >= 1) {
+        // separately allocated device polynomials (possibly in PEER memory): no staging copy, the first NTT pass
+        // follows the pointer table
+        for (size_t j = 0; j < w; j++)
+            if (!polys[j]) return fail(PCS_ERR_ARG, "NULL polynomial pointer");
+        PCS_CUDA(ptr_table.alloc(w * sizeof(uint64_t*), st));
+        PCS_CUDA(cudaMemcpyAsync(ptr_table.p, polys, w * sizeof(uint64_t*), cudaMemcpyHostToDevice, st));
     } else {
         PCS_CUDA(cudaMallocAsync((void**)&staged, w * d * 8, st));
         b->coeffs = staged;  // owned by the batch from here on
@@ -480,7 +488,8 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
             PCS_CUDA(ntt_lde_cosets(plan, src + j0 * d, d, b->lde + j0 * n, n, j1 - j0, coset_first, lg_cosets, st));
         }
     } else {
-        PCS_CUDA(ntt_lde_cosets(plan, src, d, b->lde, n, w, coset_first, lg_cosets, st));
+        PCS_CUDA(ntt_lde_cosets(plan, src, d, b->lde, n, w, coset_first, lg_cosets, st,
+                                (const uint64_t* const*)ptr_table.p));
     }
     for (size_t k = 0; k < salt_w; k++) {
         if (!salts[k]) return fail(PCS_ERR_ARG, "NULL salt pointer");

@@ -63,8 +63,11 @@ cudaError_t ntt_lde(const NttPlan* plan, const uint64_t* coeffs, size_t in_strid
                     size_t out_stride, size_t w, cudaStream_t st);
 // Same for the coset sub-range [coset_first, coset_first + 2^lg_cosets) in leaf order (shard commits):
 // out [w][d << lg_cosets].
+// coeff_ptrs_dev (optional, lg_d >= 1): DEVICE array of w per-polynomial pointers read instead of coeffs + j*in_stride;
+// the pointers may address peer GPUs' memory (read over NVLink inside the first pass, no staging copy).
 cudaError_t ntt_lde_cosets(const NttPlan* plan, const uint64_t* coeffs, size_t in_stride, uint64_t* out,
-                           size_t out_stride, size_t w, unsigned coset_first, unsigned lg_cosets, cudaStream_t st);
+                           size_t out_stride, size_t w, unsigned coset_first, unsigned lg_cosets, cudaStream_t st,
+                           const uint64_t* const* coeff_ptrs_dev = nullptr);
 // Inverse NTT WITHOUT the 1/d scaling: values [w][d] natural order -> `out` in BIT-REVERSED order; the
 // bit-reversal permutation that always follows applies ntt_plan_scale(plan).
 cudaError_t ntt_inverse_bitrev(const NttPlan* plan, const uint64_t* values, size_t in_stride, uint64_t* out,

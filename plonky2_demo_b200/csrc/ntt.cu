@@ -164,6 +164,8 @@ void ntt_plans_free() {
 // -------------------------------------------------------------------------------------------------
 struct PassArgs {
     const uint64_t* in;
+    const uint64_t* const* in_ptrs;   // first pass only, or null: per-polynomial base pointers (may be PEER memory:
+                                      // a shard reads the coefficient blocks of the other GPUs over NVLink in place)
     uint64_t* out;
     size_t in_poly_stride, out_poly_stride;
     size_t in_coset_stride, out_coset_stride;  // in: 0 for the first pass (all cosets read the coefficients)
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassArgs a) {
         const uint32_t lgroup = cg % a.lgroups, pgroup = cg / a.lgroups;
         const uint32_t poly_base = pgroup << PB;
         const size_t l_base = (size_t)lgroup << lcl;
-        const uint64_t* in_t = a.in + (size_t)c * a.in_coset_stride + h_off + l_base;
+        const size_t in_off = (size_t)c * a.in_coset_stride + h_off + l_base;
         uint64_t* out_t = a.out + (size_t)c * a.out_coset_stride + h_off + l_base;
 
         uint64_t x[32];
@@ -281,7 +283,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassArgs a) {
                 // polynomials past the end of the batch read the last one's data: their results are never stored
                 uint32_t poly = poly_base + pl1 + (xv << xsh1);
                 poly = poly < a.n_polys ? poly : a.n_polys - 1;
-                const uint64_t* pp = in_t + (size_t)poly * a.in_poly_stride + ((size_t)rlo1 << a.L) + lcol1;
+                const uint64_t* pp = (a.in_ptrs ? a.in_ptrs[poly] : a.in + (size_t)poly * a.in_poly_stride) + in_off +
+                                     ((size_t)rlo1 << a.L) + lcol1;
 #pragma unroll
                 for (int av = 0; av < (1 << K1); av++, pp += row_stride) x[(av << (5 - K1)) | xv] = *pp;
             }
@@ -375,13 +378,15 @@ static cudaError_t launch_pass_lcl(const PassArgs& a, unsigned grid, cudaStream_
 }
 
 static cudaError_t run_passes(const NttPlan* plan, const uint64_t* in, size_t in_stride, uint64_t* out,
-                              size_t out_stride, size_t w, unsigned coset_first, unsigned lg_cosets, cudaStream_t st) {
+                              size_t out_stride, size_t w, unsigned coset_first, unsigned lg_cosets, cudaStream_t st,
+                              const uint64_t* const* in_ptrs = nullptr) {
     const unsigned lg_d = plan->lg_d, r = lg_cosets;
     const size_t d = (size_t)1 << lg_d;
     if (w == 0) return cudaSuccess;
     if (lg_cosets > plan->r || ((size_t)coset_first + ((size_t)1 << lg_cosets)) > ((size_t)1 << plan->r))
         return cudaErrorInvalidValue;
     if (lg_d == 0) {
+        if (in_ptrs) return cudaErrorInvalidValue;   // callers stage single-coefficient polynomials
         size_t n = (size_t)1 << r;
         k_broadcast_const<<<(unsigned)((w * n + 255) / 256), 256, 0, st>>>(in, in_stride, out, out_stride, w, n,
                                                                           plan->scale);
@@ -393,6 +398,7 @@ static cudaError_t run_passes(const NttPlan* plan, const uint64_t* in, size_t in
         bool first = pi == 0, last = pi + 1 == plan->passes.size();
         const unsigned nb = ps.nb, k1 = nb <= 5 ? nb : (nb + 1) / 2, lc = NTT_TILE_LOG - nb;
         a.in = first ? in : out;
+        a.in_ptrs = first ? in_ptrs : nullptr;
         a.out = out;
         a.in_poly_stride = first ? in_stride : out_stride;
         a.out_poly_stride = out_stride;
@@ -453,8 +459,9 @@ cudaError_t ntt_lde(const NttPlan* plan, const uint64_t* coeffs, size_t in_strid
 }
 
 cudaError_t ntt_lde_cosets(const NttPlan* plan, const uint64_t* coeffs, size_t in_stride, uint64_t* out,
-                           size_t out_stride, size_t w, unsigned coset_first, unsigned lg_cosets, cudaStream_t st) {
-    return run_passes(plan, coeffs, in_stride, out, out_stride, w, coset_first, lg_cosets, st);
+                           size_t out_stride, size_t w, unsigned coset_first, unsigned lg_cosets, cudaStream_t st,
+                           const uint64_t* const* coeff_ptrs_dev) {
+    return run_passes(plan, coeffs, in_stride, out, out_stride, w, coset_first, lg_cosets, st, coeff_ptrs_dev);
 }
 
 cudaError_t ntt_inverse_bitrev(const NttPlan* plan, const uint64_t* values, size_t in_stride, uint64_t* out,

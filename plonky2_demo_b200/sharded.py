@@ -109,12 +109,15 @@ class CudaShardEngine:
         if _ffi.lib().pcs_stream() != torch.cuda.current_stream().cuda_stream:
             _ffi.check(_ffi.lib().pcs_synchronize())   # the all-gather that follows runs on torch's stream
 
-    def commit_shard(self, coeffs, w, plan, rank, keep_handle=True):
-        """coeffs: torch CUDA int64 tensor [>= w][d] (contiguous).  Returns (handle, local cap [2^lch][4])."""
+    def commit_shard(self, coeffs, w, plan, rank, poly_ptrs=None):
+        """coeffs: torch CUDA int64 tensor [>= w][d] (contiguous), or poly_ptrs: w raw device pointers (possibly
+        into peer GPUs' memory).  Returns (handle, local cap [2^lch][4])."""
         L = _ffi.lib()
         self._order_after_torch()
-        d = coeffs.shape[1]
-        ptrs = _ffi.dev_ptr_array(coeffs.data_ptr(), w, d)
+        if poly_ptrs is not None:
+            ptrs = (_ffi.u64p * w)(*[C.cast(C.c_void_p(int(a)), _ffi.u64p) for a in poly_ptrs])
+        else:
+            ptrs = _ffi.dev_ptr_array(coeffs.data_ptr(), w, coeffs.shape[1])
         cap = np.empty((plan.local_cap_len(), 4), dtype=np.uint64)
         h = C.c_void_p()
         _ffi.check(L.pcs_commit_shard_from_coeffs(ptrs, w, plan.lg_d, plan.rate_bits, plan.coset_first(rank), plan.lg_cosets,
@@ -156,14 +159,40 @@ class ShardedPolynomialBatch:
     def __init__(self):
         self._h = None
 
+    # ---- peer-memory exchange ---------------------------------------------------------------------------
+    _symm_cache = {}
+
+    @classmethod
+    def _symm_block(cls, group, w_max, d, device):
+        """One symmetric-memory buffer [w_max][d] per (group, shape): every rank's buffer is mapped into every
+        process (torch.distributed._symmetric_memory: cuMem + NVLink peer mapping), rendezvous happens once."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        key = (id(group), w_max, d, str(device))
+        if key not in cls._symm_cache:
+            buf = symm_mem.empty((w_max, d), dtype=torch.int64, device=device)
+            hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            cls._symm_cache[key] = (buf, hdl)
+        return cls._symm_cache[key]
+
     # ---- constructors (collective: every rank of `group` calls them) ---------------------------------
     @classmethod
-    def from_coeffs(cls, local_coeffs, n_polys, rate_bits, cap_height, group=None, engine=None, partitioned=True):
+    def from_coeffs(cls, local_coeffs, n_polys, rate_bits, cap_height, group=None, engine=None, partitioned=True,
+                    exchange="auto"):
         """oracle.rs:68-98 over a process group.
 
         partitioned=True : `local_coeffs` is this rank's block [poly_range(rank)][d] of the n_polys polynomials
                            (torch int64 tensor on the rank's device, bit pattern = u64);
         partitioned=False: every rank already holds all [n_polys][d] coefficients.
+        exchange         : how the other ranks' coefficient blocks reach this rank's LDE --
+            "allgather": NCCL all-gather into a local [W][d] matrix, then the LDE;
+            "peer"     : NO collective: every block sits in symmetric memory and the first NTT pass of each rank
+                         loads the other ranks' coefficients straight from their HBM over NVLink (fused exchange +
+                         compute, transfer hidden behind the butterflies);
+            "auto"     : "peer" when each rank extends a single coset (every coefficient is read once per rank, so
+                         reading it remotely costs no more traffic than gathering it), else "allgather".
         """
         import torch
         import torch.distributed as dist
@@ -173,7 +202,22 @@ class ShardedPolynomialBatch:
         engine = engine or CudaShardEngine()
         d = int(local_coeffs.shape[1])
         plan = ShardPlan(n_polys, log2_strict(d), rate_bits, cap_height, world)
-        if partitioned and world > 1:
+        if exchange == "auto":
+            exchange = "peer" if (plan.lg_cosets == 0 and local_coeffs.is_cuda and isinstance(engine, CudaShardEngine)) else "allgather"
+        poly_ptrs = None
+        if partitioned and world > 1 and exchange == "peer":
+            lo, hi = plan.poly_range(rank)
+            if local_coeffs.shape[0] != hi - lo:
+                raise ValueError(f"rank {rank} must hold polynomials [{lo}, {hi}), got {local_coeffs.shape[0]} rows")
+            buf, hdl = cls._symm_block(group, plan.w_max, d, local_coeffs.device)
+            buf[: hi - lo].copy_(local_coeffs)
+            hdl.barrier()                      # every rank's block is in place (stream-ordered)
+            poly_ptrs = []
+            for q in range(world):
+                qlo, qhi = plan.poly_range(q)
+                poly_ptrs += [int(hdl.buffer_ptrs[q]) + 8 * d * i for i in range(qhi - qlo)]
+            full = local_coeffs
+        elif partitioned and world > 1:
             lo, hi = plan.poly_range(rank)
             if local_coeffs.shape[0] != hi - lo:
                 raise ValueError(f"rank {rank} must hold polynomials [{lo}, {hi}), got {local_coeffs.shape[0]} rows")
@@ -192,8 +236,13 @@ class ShardedPolynomialBatch:
         self.plan, self.rank, self.world, self.group, self.engine = plan, rank, world, group, engine
         self.degree_log, self.rate_bits, self.blinding, self.cap_height = plan.lg_d, rate_bits, False, cap_height
         self.n_polys = n_polys
-        self._coeffs = full          # PolynomialBatch.polynomials (replicated)
-        self._h, local_cap = engine.commit_shard(full, n_polys, plan, rank)
+        self._coeffs = full          # PolynomialBatch.polynomials (replicated; only the local block with exchange="peer")
+        if poly_ptrs is not None:
+            self._h, local_cap = engine.commit_shard(None, n_polys, plan, rank, poly_ptrs=poly_ptrs)
+            hdl.barrier()                      # all ranks are done reading before any block is overwritten
+        else:
+            self._h, local_cap = engine.commit_shard(full, n_polys, plan, rank)
+        self.exchange = exchange if (partitioned and world > 1) else "none"
         # exchange step 2: all-gather of the local caps
         if world > 1:
             mine = torch.from_numpy(local_cap.view(np.int64)).to(full.device)

@@ -210,6 +210,33 @@ def test_cuda_shards_assemble_to_reference(w, lg_d, r, cap, world):
 
 
 @pytest.mark.gpu
+def test_cuda_commit_from_scattered_device_pointers():
+    """PCS_DEVICE_PTRS with separately allocated polynomials: the first NTT pass follows the pointer table (the path a
+    shard uses to read peer GPUs' coefficient blocks in place); result == contiguous commit == oracle."""
+    import ctypes as C
+
+    import torch
+
+    import plonky2_demo_b200 as p
+    from plonky2_demo_b200 import _ffi
+
+    p.init(0)
+    for w, lg_d, r, cap in [(9, 12, 3, 4), (135, 10, 3, 4), (3, 1, 2, 0), (20, 15, 1, 2)]:
+        coeffs = seeded_polys(w, 1 << lg_d, base_seed=91)
+        ref = oracle.commit_from_coeffs(coeffs, r, cap)
+        rows = [torch.from_numpy(coeffs[j].view(np.int64).copy()).cuda() for j in reversed(range(w))][::-1]  # scattered allocations
+        ptrs = (_ffi.u64p * w)(*[C.cast(C.c_void_p(t.data_ptr()), _ffi.u64p) for t in rows])
+        cap_out = np.empty((1 << cap, 4), dtype=np.uint64)
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().pcs_commit_from_coeffs(ptrs, w, lg_d, r, cap, None, 0, _ffi.PCS_DEVICE_PTRS, _ffi.ptr(cap_out), C.byref(h)))
+        assert np.array_equal(cap_out, ref["cap"])
+        dig = np.empty_like(ref["digests"])
+        _ffi.check(_ffi.lib().pcs_batch_digests(h, _ffi.ptr(dig)))
+        assert np.array_equal(dig, ref["digests"])
+        _ffi.lib().pcs_batch_free(h)
+
+
+@pytest.mark.gpu
 def test_cuda_intt_dev_matches_oracle():
     import torch
 

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--rate-bits", type=int, default=3)
     ap.add_argument("--cap-height", type=int, default=4)
     ap.add_argument("--samples", type=int, default=3)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer"])
     ap.add_argument("--eval-polys", type=int, default=4, help="polynomials evaluated directly on the CPU per sampled leaf")
     a = ap.parse_args()
 
@@ -68,7 +69,7 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        batch = ShardedPolynomialBatch.from_coeffs(local_coeffs, w, r, cap_h, partitioned=True)
+        batch = ShardedPolynomialBatch.from_coeffs(local_coeffs, w, r, cap_h, partitioned=True, exchange=a.exchange)
         e1.record(stream)
         dist.barrier()
         torch.cuda.synchronize()
@@ -100,6 +101,7 @@ def main():
         best = min(times)
         print(json.dumps({
             "config": f"large commit: {w} polys x 2^{lg_d}, rate_bits {r}, cap_height {cap_h}, sharded over {world} GPUs",
+            "exchange": batch.exchange,
             "ms": times, "best_ms": best, "elems_per_s": elems / (best * 1e-3), "lde_bytes": elems * 8,
             "sampled_leaves": leaves, "merkle_paths_verify_against_cap": bool(ok_paths),
             "rows_equal_direct_cpu_evaluation": bool(flag.item()), "polys_evaluated_per_rank": min(a.eval_polys, hi - lo),
