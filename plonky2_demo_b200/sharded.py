@@ -191,8 +191,10 @@ class ShardedPolynomialBatch:
             "peer"     : NO collective: every block sits in symmetric memory and the first NTT pass of each rank
                          loads the other ranks' coefficients straight from their HBM over NVLink (fused exchange +
                          compute, transfer hidden behind the butterflies);
-            "auto"     : "peer" when each rank extends a single coset (every coefficient is read once per rank, so
-                         reading it remotely costs no more traffic than gathering it), else "allgather".
+            "auto"     : "allgather".  Measured on 8 x B200 (135 x 2^20, one coset per rank, profiles/r01_scaling_v5.md):
+                         the peer-reading LDE costs 3.41 ms against 2.72 ms + ~1.4 ms of all-gather, but the two
+                         cross-rank barriers and the symmetric-buffer copy it needs cost more than that on the
+                         host side (21.9 ms vs 18.3 ms per commitment), so the collective stays the default.
         """
         import torch
         import torch.distributed as dist
@@ -203,7 +205,7 @@ class ShardedPolynomialBatch:
         d = int(local_coeffs.shape[1])
         plan = ShardPlan(n_polys, log2_strict(d), rate_bits, cap_height, world)
         if exchange == "auto":
-            exchange = "peer" if (plan.lg_cosets == 0 and local_coeffs.is_cuda and isinstance(engine, CudaShardEngine)) else "allgather"
+            exchange = "allgather"
         poly_ptrs = None
         if partitioned and world > 1 and exchange == "peer":
             lo, hi = plan.poly_range(rank)
