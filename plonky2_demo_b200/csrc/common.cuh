@@ -39,7 +39,7 @@ cudaError_t launch_permute(uint64_t* states, size_t n, cudaStream_t st);
 // (merkle_tree.rs:43-51) or into cap when the subtree is a single leaf.
 cudaError_t launch_leaf_hash_cols(const uint64_t* cols, size_t col_stride, uint32_t width, size_t n_leaves,
                                   unsigned lg_sub /*log2 leaves per cap subtree*/, uint64_t* digests,
-                                  uint64_t* cap, cudaStream_t st);
+                                  uint64_t* cap, cudaStream_t st, size_t first_leaf = 0, size_t leaf_count = (size_t)-1);
 // Plain variant: digest i -> out[i*4..] (pcs_hash_or_noop)
 cudaError_t launch_hash_cols_plain(const uint64_t* cols, size_t col_stride, uint32_t width, size_t n,
                                    uint64_t* out, cudaStream_t st);

@@ -13,9 +13,9 @@ namespace pcs {
 
 // tree_mode: digest of leaf i goes to its tree slot (or cap); otherwise to out[4*i].
 __global__ void __launch_bounds__(HASH_THREADS)
-k_hash_cols(const uint64_t* __restrict__ cols, size_t col_stride, uint32_t width, size_t n, int tree_mode,
+k_hash_cols(const uint64_t* __restrict__ cols, size_t col_stride, uint32_t width, size_t first, size_t n, int tree_mode,
             unsigned lg_sub, uint64_t* __restrict__ digests, uint64_t* __restrict__ cap) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // leaves [first, n) of the tree
     if (i >= n) return;
     uint64_t d[4];
     const uint64_t* p = cols + i;
@@ -44,17 +44,19 @@ k_hash_cols(const uint64_t* __restrict__ cols, size_t col_stride, uint32_t width
 }
 
 cudaError_t launch_leaf_hash_cols(const uint64_t* cols, size_t col_stride, uint32_t width, size_t n_leaves,
-                                  unsigned lg_sub, uint64_t* digests, uint64_t* cap, cudaStream_t st) {
-    if (n_leaves == 0) return cudaSuccess;
-    k_hash_cols<<<grid_for(n_leaves, HASH_THREADS), HASH_THREADS, 0, st>>>(cols, col_stride, width, n_leaves, 1,
-                                                                          lg_sub, digests, cap);
+                                  unsigned lg_sub, uint64_t* digests, uint64_t* cap, cudaStream_t st,
+                                  size_t first_leaf, size_t leaf_count) {
+    if (leaf_count == (size_t)-1) leaf_count = n_leaves - first_leaf;
+    if (leaf_count == 0) return cudaSuccess;
+    k_hash_cols<<<grid_for(leaf_count, HASH_THREADS), HASH_THREADS, 0, st>>>(cols, col_stride, width, first_leaf,
+                                                                            first_leaf + leaf_count, 1, lg_sub, digests, cap);
     return cudaGetLastError();
 }
 
 cudaError_t launch_hash_cols_plain(const uint64_t* cols, size_t col_stride, uint32_t width, size_t n,
                                    uint64_t* out, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    k_hash_cols<<<grid_for(n, HASH_THREADS), HASH_THREADS, 0, st>>>(cols, col_stride, width, n, 0, 0, out, nullptr);
+    k_hash_cols<<<grid_for(n, HASH_THREADS), HASH_THREADS, 0, st>>>(cols, col_stride, width, 0, n, 0, 0, out, nullptr);
     return cudaGetLastError();
 }
 
