@@ -146,6 +146,8 @@ PCS_API int pcs_batch_get_rows(const pcs_batch* b, const uint64_t* leaf_indices,
 PCS_API int pcs_batch_prove(const pcs_batch* b, size_t leaf_index, uint64_t* siblings);
 /* polynomials[i].coeffs (needs PCS_KEEP_COEFFS or from_values).                                     */
 PCS_API int pcs_batch_coeffs(const pcs_batch* b, size_t poly, uint64_t* coeffs /*[d]*/);
+/* All of `polynomials` at once as one [w][d] matrix.                                                  */
+PCS_API int pcs_batch_all_coeffs(const pcs_batch* b, uint64_t* coeffs /*[w][d]*/);
 /* Device views (valid until pcs_batch_free): LDE is [leaf_len][N] poly-major in leaf order.        */
 PCS_API const uint64_t* pcs_batch_lde_dev(const pcs_batch* b);
 PCS_API const uint64_t* pcs_batch_digests_dev(const pcs_batch* b);

@@ -40,6 +40,7 @@ SIGNATURES = {
     "pcs_batch_get_rows": (C.c_int, [C.c_void_p, u64p, sz, u64p]),
     "pcs_batch_prove": (C.c_int, [C.c_void_p, sz, u64p]),
     "pcs_batch_coeffs": (C.c_int, [C.c_void_p, sz, u64p]),
+    "pcs_batch_all_coeffs": (C.c_int, [C.c_void_p, u64p]),
     "pcs_batch_lde_dev": (C.c_void_p, [C.c_void_p]),
     "pcs_batch_digests_dev": (C.c_void_p, [C.c_void_p]),
     "pcs_batch_cap_dev": (C.c_void_p, [C.c_void_p]),

@@ -23,6 +23,10 @@ struct Ctx {
     bool own_stream = false;
     // host-input pipeline: H2D copies run on their own stream, one event per chunk of polynomials,
     // so that the LDE of chunk k overlaps the PCIe transfer of chunk k+1
+    // small host inputs / outputs (polynomials of a few KB): gathered through pinned staging so that W tiny copies
+    // become one (a cudaMemcpyAsync call costs more than moving 64 bytes)
+    void* pin_in = nullptr;  size_t pin_in_bytes = 0;
+    void* pin_out = nullptr; size_t pin_out_bytes = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_sync = nullptr;
     std::vector<cudaEvent_t> chunk_ev;
@@ -140,6 +144,8 @@ void pcs_shutdown(void) {
     drain_pending();
     ntt_plans_free();
     if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
+    if (g_ctx.pin_in) cudaFreeHost(g_ctx.pin_in);
+    if (g_ctx.pin_out) cudaFreeHost(g_ctx.pin_out);
     if (g_ctx.ev_sync) cudaEventDestroy(g_ctx.ev_sync);
     for (auto& e : g_ctx.chunk_ev) cudaEventDestroy(e);
     if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.stream);
@@ -275,6 +281,23 @@ int pcs_ntt_dev(uint64_t* polys_dev, size_t w, unsigned lg_n, int inverse) {
     PCS_CUDA(ntt_lde(plan, polys_dev, n, b.u64(), n, w, st));                                              // -> bit-reversed
     PCS_CUDA(launch_bitrev_permute(b.u64(), n, polys_dev, n, w, lg_n, st, ntt_plan_scale(plan)));          // -> natural
     return PCS_OK;   // asynchronous on pcs_stream()
+}
+
+constexpr size_t SMALL_POLY_BYTES = 32 * 1024;     // below this, host polynomials go through pinned staging
+constexpr size_t PIN_STAGING_MAX = 64u << 20;
+
+static void* pinned(void*& buf, size_t& cap, size_t bytes) {
+    if (bytes > cap) {
+        if (buf) cudaFreeHost(buf);
+        buf = nullptr;
+        cap = 0;
+        if (cudaHostAlloc(&buf, bytes, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        cap = bytes;
+    }
+    return buf;
 }
 
 // gather w separately allocated host/device polynomials into one [w][d] device matrix
@@ -421,6 +444,7 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
     const uint64_t* src = nullptr;   // [w][d] device input (values or coefficients)
     DevBuf ptr_table;                // or: device table of the caller's w polynomial pointers, read in place
     uint64_t* staged = nullptr;
+    bool scatter_coeffs = false;
     constexpr size_t H2D_CHUNK = 16;  // polynomials per H2D chunk
     size_t n_chunks = 0;              // > 0: host inputs arrive chunk by chunk on the copy stream
     if (contiguous_dev && !from_values && !(flags & PCS_KEEP_COEFFS)) {
@@ -440,6 +464,14 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
         else if (dev_ptrs) {
             int rc = stage_polys(polys, w, d, true, staged, st);
             if (rc) return rc;
+        } else if (d * 8 <= SMALL_POLY_BYTES && w * d * 8 <= PIN_STAGING_MAX &&
+                   pinned(g_ctx.pin_in, g_ctx.pin_in_bytes, w * d * 8)) {
+            // small host polynomials: one gather on the host, one H2D copy
+            for (size_t j = 0; j < w; j++) {
+                if (!polys[j]) return fail(PCS_ERR_ARG, "NULL polynomial pointer");
+                memcpy((char*)g_ctx.pin_in + j * d * 8, polys[j], d * 8);
+            }
+            PCS_CUDA(cudaMemcpyAsync(staged, g_ctx.pin_in, w * d * 8, cudaMemcpyHostToDevice, st));
         } else {
             // host inputs: chunked H2D on the copy stream, one event per chunk
             if (!g_ctx.copy_stream) PCS_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
@@ -473,10 +505,17 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
         // values (natural) -> coefficients in bit-reversed order (scratch = head of the LDE buffer)
         PCS_CUDA(ntt_inverse_bitrev(iplan, src, d, b->lde, d, w, st));
         PCS_CUDA(launch_bitrev_permute(b->lde, d, staged, d, w, lg_d, st, ntt_plan_scale(iplan)));  // -> natural order (+ 1/d), in `staged`
-        if (coeffs_out)
-            for (size_t j = 0; j < w; j++)
-                if (coeffs_out[j])
-                    PCS_CUDA(cudaMemcpyAsync(coeffs_out[j], staged + j * d, d * 8, cudaMemcpyDeviceToHost, st));
+        if (coeffs_out) {
+            if (d * 8 <= SMALL_POLY_BYTES && w * d * 8 <= PIN_STAGING_MAX &&
+                pinned(g_ctx.pin_out, g_ctx.pin_out_bytes, w * d * 8)) {
+                PCS_CUDA(cudaMemcpyAsync(g_ctx.pin_out, staged, w * d * 8, cudaMemcpyDeviceToHost, st));
+                scatter_coeffs = true;   // scattered to the caller's vectors after the final synchronisation
+            } else {
+                for (size_t j = 0; j < w; j++)
+                    if (coeffs_out[j])
+                        PCS_CUDA(cudaMemcpyAsync(coeffs_out[j], staged + j * d, d * 8, cudaMemcpyDeviceToHost, st));
+            }
+        }
     }
     PCS_CUDA(cudaEventRecord(b->ev[1], st));
 
@@ -520,9 +559,12 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
     if (cap_out) {
         PCS_CUDA(cudaMemcpyAsync(cap_out, b->cap, n_cap * 32, cudaMemcpyDeviceToHost, st));
         PCS_CUDA(cudaStreamSynchronize(st));
-    } else if (!dev_ptrs) {
+    } else if (!dev_ptrs || scatter_coeffs) {
         PCS_CUDA(cudaStreamSynchronize(st));  // host inputs must not be reused before the copies finish
     }
+    if (scatter_coeffs)
+        for (size_t j = 0; j < w; j++)
+            if (coeffs_out[j]) memcpy(coeffs_out[j], (char*)g_ctx.pin_out + j * d * 8, d * 8);
     guard.armed = false;
     b->committed = true;
     *out = b;
@@ -634,6 +676,15 @@ int pcs_batch_coeffs(const pcs_batch* b, size_t poly, uint64_t* coeffs) {
     cudaStream_t st = g_ctx.stream;
     size_t d = (size_t)1 << b->lg_d;
     PCS_CUDA(cudaMemcpyAsync(coeffs, b->coeffs + poly * d, d * 8, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+int pcs_batch_all_coeffs(const pcs_batch* b, uint64_t* coeffs) {
+    if (!b || !coeffs) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (!b->coeffs) return fail(PCS_ERR_ARG, "coefficients were not kept (PCS_KEEP_COEFFS)");
+    cudaStream_t st = g_ctx.stream;
+    PCS_CUDA(cudaMemcpyAsync(coeffs, b->coeffs, (b->w << b->lg_d) * 8, cudaMemcpyDeviceToHost, st));
     PCS_CUDA(cudaStreamSynchronize(st));
     return PCS_OK;
 }

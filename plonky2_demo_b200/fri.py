@@ -217,11 +217,11 @@ class PolynomialBatch:
         sp = _ffi.ptr_array(salt_rows) if salt_rows else None
         L = _ffi.lib()
         if is_values:
-            coeffs = np.empty((len(rows), d), dtype=np.uint64)
-            cp = _ffi.ptr_array([coeffs[j] for j in range(len(rows))])
+            # the coefficients stay on the device with the batch (PCS_KEEP_COEFFS) and are fetched when
+            # `polynomials` is first read, like the leaves
             rc = L.pcs_commit_from_values(pp, len(rows), lg_d, rate_bits, cap_height, sp, len(salt_rows),
-                                          _ffi.PCS_KEEP_COEFFS, cp, _ffi.ptr(cap), C.byref(h))
-            self._coeffs_host = coeffs
+                                          _ffi.PCS_KEEP_COEFFS, None, _ffi.ptr(cap), C.byref(h))
+            self._coeffs_host = None
         else:
             rc = L.pcs_commit_from_coeffs(pp, len(rows), lg_d, rate_bits, cap_height, sp, len(salt_rows),
                                           0, _ffi.ptr(cap), C.byref(h))
@@ -246,6 +246,10 @@ class PolynomialBatch:
     @property
     def polynomials(self):
         """oracle.rs:33: Vec<PolynomialCoeffs<F>> (coefficient form)."""
+        if self._coeffs_host is None:
+            out = np.empty((self.n_polys, 1 << self.degree_log), dtype=np.uint64)
+            _ffi.check(_ffi.lib().pcs_batch_all_coeffs(self._h, _ffi.ptr(out)))
+            self._coeffs_host = out
         return [PolynomialCoeffs(c) for c in self._coeffs_host]
 
     def get_rows(self, indices):
