@@ -493,42 +493,51 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
                 }
                 PCS_CUDA(cudaEventRecord(g_ctx.chunk_ev[k], g_ctx.copy_stream));
             }
-            if (from_values)   // the IFFT below runs over the whole batch
-                PCS_CUDA(cudaStreamWaitEvent(st, g_ctx.chunk_ev[n_chunks - 1], 0));
         }
         src = staged;
     }
     PCS_CUDA(cudaEventRecord(b->ev[0], st));
 
-    // ---- "IFFT" (oracle.rs:51-55) ----
-    if (from_values) {
-        // values (natural) -> coefficients in bit-reversed order (scratch = head of the LDE buffer)
-        PCS_CUDA(ntt_inverse_bitrev(iplan, src, d, b->lde, d, w, st));
-        PCS_CUDA(launch_bitrev_permute(b->lde, d, staged, d, w, lg_d, st, ntt_plan_scale(iplan)));  // -> natural order (+ 1/d), in `staged`
-        if (coeffs_out) {
-            if (d * 8 <= SMALL_POLY_BYTES && w * d * 8 <= PIN_STAGING_MAX &&
-                pinned(g_ctx.pin_out, g_ctx.pin_out_bytes, w * d * 8)) {
-                PCS_CUDA(cudaMemcpyAsync(g_ctx.pin_out, staged, w * d * 8, cudaMemcpyDeviceToHost, st));
-                scatter_coeffs = true;   // scattered to the caller's vectors after the final synchronisation
-            } else {
-                for (size_t j = 0; j < w; j++)
-                    if (coeffs_out[j])
-                        PCS_CUDA(cudaMemcpyAsync(coeffs_out[j], staged + j * d, d * 8, cudaMemcpyDeviceToHost, st));
-            }
-        }
+    // ---- "IFFT" (oracle.rs:51-55) for polynomials [j0, j1): values (natural order) -> coefficients in `staged` ----
+    // scratch for the bit-reversed intermediate = the TAIL of the LDE buffer (the last w*d elements): LDE rows already
+    // written for earlier polynomials end at j0*n <= wt*n - w*d + j0*d, so chunk-by-chunk processing never clobbers them
+    uint64_t* const ifft_scratch = b->lde + (wt * n - w * d);
+    const bool small_out = from_values && coeffs_out && d * 8 <= SMALL_POLY_BYTES && w * d * 8 <= PIN_STAGING_MAX &&
+                           pinned(g_ctx.pin_out, g_ctx.pin_out_bytes, w * d * 8);
+    auto ifft_range = [&](size_t j0, size_t j1) -> int {
+        PCS_CUDA(ntt_inverse_bitrev(iplan, src + j0 * d, d, ifft_scratch + j0 * d, d, j1 - j0, st));
+        PCS_CUDA(launch_bitrev_permute(ifft_scratch + j0 * d, d, staged + j0 * d, d, j1 - j0, lg_d, st, ntt_plan_scale(iplan)));
+        if (coeffs_out && !small_out)
+            for (size_t j = j0; j < j1; j++)
+                if (coeffs_out[j])
+                    PCS_CUDA(cudaMemcpyAsync(coeffs_out[j], staged + j * d, d * 8, cudaMemcpyDeviceToHost, st));
+        return PCS_OK;
+    };
+    const bool chunked = n_chunks > 0;   // host inputs arriving chunk by chunk: IFFT and LDE follow each chunk
+    if (from_values && !chunked) {
+        int rc = ifft_range(0, w);
+        if (rc) return rc;
     }
     PCS_CUDA(cudaEventRecord(b->ev[1], st));
 
     // ---- "FFT + blinding" (oracle.rs:100-125), output already in leaf order ----
-    if (n_chunks && !from_values) {
+    if (chunked) {
         for (size_t k = 0; k < n_chunks; k++) {
             size_t j0 = k * H2D_CHUNK, j1 = j0 + H2D_CHUNK < w ? j0 + H2D_CHUNK : w;
             PCS_CUDA(cudaStreamWaitEvent(st, g_ctx.chunk_ev[k], 0));
+            if (from_values) {
+                int rc = ifft_range(j0, j1);
+                if (rc) return rc;
+            }
             PCS_CUDA(ntt_lde_cosets(plan, src + j0 * d, d, b->lde + j0 * n, n, j1 - j0, coset_first, lg_cosets, st));
         }
     } else {
         PCS_CUDA(ntt_lde_cosets(plan, src, d, b->lde, n, w, coset_first, lg_cosets, st,
                                 (const uint64_t* const*)ptr_table.p));
+    }
+    if (small_out) {
+        PCS_CUDA(cudaMemcpyAsync(g_ctx.pin_out, staged, w * d * 8, cudaMemcpyDeviceToHost, st));
+        scatter_coeffs = true;   // scattered to the caller's vectors after the final synchronisation
     }
     for (size_t k = 0; k < salt_w; k++) {
         if (!salts[k]) return fail(PCS_ERR_ARG, "NULL salt pointer");

@@ -225,6 +225,7 @@ COMMIT_SHAPES = [
     (8, 11, 3, 4),     # two passes
     (135, 12, 3, 4),
     (3, 14, 3, 4),
+    (33, 13, 3, 4),    # host polynomials > 32 KB, 3 H2D chunks: pipelined copy / LDE path
 ]
 
 
@@ -254,7 +255,7 @@ def test_from_coeffs(pcs, w, lg_d, rate_bits, cap_height):
     b.free()
 
 
-@pytest.mark.parametrize("w,lg_d,rate_bits,cap_height", [(135, 3, 3, 4), (7, 6, 3, 2), (20, 10, 3, 4), (5, 12, 2, 4), (1, 0, 2, 1)])
+@pytest.mark.parametrize("w,lg_d,rate_bits,cap_height", [(135, 3, 3, 4), (7, 6, 3, 2), (20, 10, 3, 4), (5, 12, 2, 4), (1, 0, 2, 1), (40, 14, 3, 4)])
 def test_from_values(pcs, w, lg_d, rate_bits, cap_height):
     d = 1 << lg_d
     rng = np.random.default_rng(lg_d)
