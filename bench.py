@@ -41,8 +41,8 @@ import numpy as np  # noqa: E402
 METRIC = "lde_merkle_commit_elems_per_s"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_hash_cols launch from an `ncu --set full` capture of this
 # very command, keyed by (width, lg_d, rate_bits, n_gpus); None where no capture exists.
-NCU_TRAFFIC = {(135, 20, 3, 1): 9079874000 + 272440320}
-NCU_TRAFFIC_SOURCE = "profiles/r01_leafhash_v4.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+NCU_TRAFFIC = {(135, 20, 3, 1): 9082833000 + 273173248}
+NCU_TRAFFIC_SOURCE = "profiles/r01_leafhash_v5.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
 UNIT = "elems/s"
 
 

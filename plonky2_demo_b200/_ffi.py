@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcs.so")
+LIB_PATH = os.environ.get("PCS_LIB") or os.path.join(_HERE, "libpcs.so")   # PCS_LIB: A/B builds of the same engine
 
 u64p = C.POINTER(C.c_uint64)
 u64pp = C.POINTER(u64p)

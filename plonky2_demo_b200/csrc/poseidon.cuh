@@ -307,8 +307,23 @@ __device__ __forceinline__ void partial_round_d(uint64_t& x0, double (&dl)[12], 
 // layer (tests/golden/make_golden.py:round_addends); it is absorbed by 3-input adds of the network.
 __device__ __forceinline__ void full_round(uint64_t (&s)[12], int r) {
     using namespace pconst;
+#if PCS_SBOX_GROUP == 12
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
+#else
+    // S-box layer as a rolled loop over groups of lanes (the state rotates by one group per pass): smaller code for
+    // the instruction cache at the price of 2 register moves per lane per pass
+#pragma unroll 1
+    for (int g = 0; g < 12 / PCS_SBOX_GROUP; g++) {
+        uint64_t t[PCS_SBOX_GROUP];
+#pragma unroll
+        for (int i = 0; i < PCS_SBOX_GROUP; i++) t[i] = sbox7(s[i]);
+#pragma unroll
+        for (int i = 0; i < 12 - PCS_SBOX_GROUP; i++) s[i] = s[i + PCS_SBOX_GROUP];
+#pragma unroll
+        for (int i = 0; i < PCS_SBOX_GROUP; i++) s[12 - PCS_SBOX_GROUP + i] = t[i];
+    }
+#endif
 #if PCS_MDS_FP64
     mds_layer_fp64(s, &ROUND_ADD_D[24 * r]);
 #else
