@@ -362,11 +362,13 @@ constexpr int lcl_max(int k1, int k2) { return (13 - k1 - k2) < (8 - k1) ? (13 -
 template <int K1, int K2, int LCL>
 static cudaError_t launch_pass(const PassArgs& a, unsigned grid, cudaStream_t st) {
     constexpr size_t smem = ((size_t)(1u << NTT_TILE_LOG) + 16 * K1 + 512 * K2 + 16) * sizeof(uint64_t);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static int attr_dev = -1;   // the opt-in to > 48 KB of dynamic shared memory is per device
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
         cudaError_t e = cudaFuncSetAttribute(k_ntt_pass<K1, K2, LCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_dev = dev;
     }
     k_ntt_pass<K1, K2, LCL><<<grid, NTT_THREADS, smem, st>>>(a);
     return cudaGetLastError();
