@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--cpu-sample-lg-d", type=int, default=16, help="degree_log of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chunks", type=int, default=2,
+                    help="N > 1: polynomial groups of the streaming exchange (1 = one all-gather, then the LDE)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer"],
                     help="N > 1: how coefficient blocks reach the other ranks (plonky2_demo_b200/sharded.py)")
     return ap.parse_args()
@@ -222,14 +224,15 @@ def run_ours(a):
     # polynomials; world > 1: this rank's block of the same W polynomials (plonky2_demo_b200/sharded.py)
     from plonky2_demo_b200.sharded import ShardedPolynomialBatch, ShardPlan
 
-    plan = ShardPlan(w, lg_d, r, cap_h, world)
-    p_lo, p_hi = plan.poly_range(rank) if world > 1 else (0, w)
-    w_loc = p_hi - p_lo
+    chunks = a.chunks if a.exchange != "peer" else 1
+    plan = ShardPlan(w, lg_d, r, cap_h, world, chunks if world > 1 else 1)
+    my_polys = plan.local_polys(rank) if world > 1 else list(range(w))
+    w_loc = len(my_polys)
     host = torch.empty((w_loc, d), dtype=torch.int64, pin_memory=True)
     host_np = host.numpy().view(np.uint64)
     from helpers import splitmix64_stream
-    for j in range(w_loc):
-        host_np[j] = splitmix64_stream(0x5EED0000 + p_lo + j, d)
+    for j, pj in enumerate(my_polys):
+        host_np[j] = splitmix64_stream(0x5EED0000 + pj, d)
     dev_coeffs = host.to(dev, non_blocking=False)
     cap_host = np.empty((1 << cap_h, 4), dtype=np.uint64)
     dev_ptrs = _ffi.dev_ptr_array(dev_coeffs.data_ptr(), w_loc, d)
@@ -253,14 +256,17 @@ def run_ours(a):
 
     def commit_device():
         if world > 1:
-            return _Sharded(ShardedPolynomialBatch.from_coeffs(dev_coeffs, w, r, cap_h, partitioned=True, exchange=a.exchange))
+            return _Sharded(ShardedPolynomialBatch.from_coeffs(dev_coeffs, w, r, cap_h, partitioned=True, exchange=a.exchange,
+                                                               chunks=plan.chunks))
         h = C.c_void_p()
         _ffi.check(L.pcs_commit_from_coeffs(dev_ptrs, w, lg_d, r, cap_h, None, 0, _ffi.PCS_DEVICE_PTRS, None, C.byref(h)))
         return h
 
     def commit_host():
         if world > 1:
-            b = ShardedPolynomialBatch.from_coeffs(host.to(dev, non_blocking=True), w, r, cap_h, partitioned=True, exchange=a.exchange)
+            # streaming exchange: the pinned host block goes in as it is, chunk c+1 crosses PCIe / NVLink under the LDE of chunk c
+            src = host if plan.chunks > 1 else host.to(dev, non_blocking=True)
+            b = ShardedPolynomialBatch.from_coeffs(src, w, r, cap_h, partitioned=True, exchange=a.exchange, chunks=plan.chunks)
             cap_host[:] = b.cap
             return _Sharded(b)
         h = C.c_void_p()

@@ -124,6 +124,14 @@ PCS_API int pcs_commit_shard_from_coeffs(const uint64_t* const* polys, size_t w,
                                  unsigned coset_first, unsigned lg_cosets, unsigned local_cap_height,
                                  const uint64_t* const* salts, size_t salt_w, unsigned flags, uint64_t* cap_out,
                                  pcs_batch** out);
+/* The same shard commit with the polynomials arriving in groups (DEVICE pointers, contiguous or scattered, possibly in
+ * peer memory): begin allocates the shard, every extend runs the coset LDE of polynomials [poly_first, poly_first+count)
+ * asynchronously on pcs_stream() -- e.g. while the next chunk of an all-gather or H2D copy is still in flight -- and
+ * finish hashes the leaves, builds the subtrees and returns the local cap.  Every polynomial must be supplied once. */
+PCS_API int pcs_shard_begin(size_t w, unsigned lg_d, unsigned rate_bits, unsigned coset_first, unsigned lg_cosets,
+                    unsigned local_cap_height, pcs_batch** out);
+PCS_API int pcs_shard_extend(pcs_batch* b, size_t poly_first, size_t count, const uint64_t* const* polys_dev);
+PCS_API int pcs_shard_finish(pcs_batch* b, uint64_t* cap_out /*NULL or [2^local_cap_height][4]*/);
 /* PolynomialBatch::from_values: IFFT every column first.                         oracle.rs:43-65
  *   coeffs_out : NULL, or w host pointers receiving the d coefficients of each polynomial
  *                (the reference keeps them as `polynomials`).                                      */

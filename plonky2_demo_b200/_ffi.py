@@ -32,6 +32,9 @@ SIGNATURES = {
     "pcs_merkle_build": (C.c_int, [u64p, sz, sz, C.c_uint, u64p, u64p]),
     "pcs_commit_from_coeffs": (C.c_int, [u64pp, sz, C.c_uint, C.c_uint, C.c_uint, u64pp, sz, C.c_uint, u64p, C.POINTER(C.c_void_p)]),
     "pcs_commit_shard_from_coeffs": (C.c_int, [u64pp, sz, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, u64pp, sz, C.c_uint, u64p, C.POINTER(C.c_void_p)]),
+    "pcs_shard_begin": (C.c_int, [sz, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_void_p)]),
+    "pcs_shard_extend": (C.c_int, [C.c_void_p, sz, sz, u64pp]),
+    "pcs_shard_finish": (C.c_int, [C.c_void_p, u64p]),
     "pcs_commit_from_values": (C.c_int, [u64pp, sz, C.c_uint, C.c_uint, C.c_uint, u64pp, sz, C.c_uint, u64pp, u64p, C.POINTER(C.c_void_p)]),
     "pcs_batch_shape": (C.c_int, [C.c_void_p, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(C.c_uint)]),
     "pcs_batch_cap": (C.c_int, [C.c_void_p, u64p]),

@@ -84,7 +84,8 @@ using namespace pcs;
 
 struct pcs_batch {
     size_t w = 0, salt_w = 0;
-    unsigned lg_d = 0, rate_bits = 0, cap_height = 0;
+    unsigned lg_d = 0, rate_bits = 0, cap_height = 0;   // rate_bits = log2(coset blocks held) for a shard
+    unsigned full_rate_bits = 0, coset_first = 0;       // the LDE this batch is (a shard of)
     size_t n = 0;          // N = d << rate_bits
     size_t n_digests = 0;  // 2 (N - 2^cap)
     uint64_t* coeffs = nullptr;   // [w][d] or null
@@ -592,6 +593,89 @@ int pcs_commit_shard_from_coeffs(const uint64_t* const* polys, size_t w, unsigne
                                  pcs_batch** out) {
     return commit_common(polys, false, w, lg_d, rate_bits, local_cap_height, salts, salt_w, flags, nullptr, cap_out, out,
                          true, coset_first, lg_cosets);
+}
+
+// ---- streaming shard commit: the polynomials arrive in groups (e.g. chunks of an all-gather still in flight) ----
+int pcs_shard_begin(size_t w, unsigned lg_d, unsigned rate_bits, unsigned coset_first, unsigned lg_cosets,
+                    unsigned local_cap_height, pcs_batch** out) {
+    PCS_NEED_INIT();
+    if (!out) return fail(PCS_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (w == 0) return fail(PCS_ERR_ARG, "empty batch (oracle.rs:76 polynomials[0])");
+    if (lg_d + rate_bits > 32) return fail(PCS_ERR_TWO_ADICITY, "n_log <= TWO_ADICITY violated");
+    if (lg_cosets > rate_bits || ((size_t)coset_first + ((size_t)1 << lg_cosets)) > ((size_t)1 << rate_bits))
+        return fail(PCS_ERR_ARG, "coset range outside [0, 2^rate_bits)");
+    unsigned lg_n = lg_d + lg_cosets;
+    if (local_cap_height > lg_n)
+        return fail(PCS_ERR_CAP_HEIGHT, "cap_height=" + std::to_string(local_cap_height) +
+                                            " should be at most log2(leaves.len())=" + std::to_string(lg_n));
+    cudaStream_t st = g_ctx.stream;
+    if (!ntt_plan_get(lg_d, rate_bits, false, 7, st)) return fail(PCS_ERR_ALLOC, "twiddle table allocation failed");
+    const size_t n = (size_t)1 << lg_n, n_cap = (size_t)1 << local_cap_height;
+    pcs_batch* b = new pcs_batch();
+    b->w = w; b->lg_d = lg_d; b->rate_bits = lg_cosets; b->cap_height = local_cap_height;
+    b->full_rate_bits = rate_bits; b->coset_first = coset_first;
+    b->n = n; b->n_digests = 2 * (n - n_cap);
+    struct Guard { pcs_batch* b; bool armed = true; ~Guard() { if (armed) pcs_batch_free(b); } } guard{b};
+    for (auto& e : b->ev) PCS_CUDA(cudaEventCreate(&e));
+    PCS_CUDA(cudaMallocAsync((void**)&b->lde, w * n * 8, st));
+    PCS_CUDA(cudaMallocAsync((void**)&b->digests, b->n_digests ? b->n_digests * 32 : 32, st));
+    PCS_CUDA(cudaMallocAsync((void**)&b->cap, n_cap * 32, st));
+    PCS_CUDA(cudaEventRecord(b->ev[0], st));
+    PCS_CUDA(cudaEventRecord(b->ev[1], st));
+    guard.armed = false;
+    *out = b;
+    return PCS_OK;
+}
+
+int pcs_shard_extend(pcs_batch* b, size_t poly_first, size_t count, const uint64_t* const* polys) {
+    if (!b || !polys) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (b->committed) return fail(PCS_ERR_ARG, "batch already finished");
+    if (poly_first + count > b->w) return fail(PCS_ERR_ARG, "polynomial range out of bounds");
+    if (count == 0) return PCS_OK;
+    cudaStream_t st = g_ctx.stream;
+    const size_t d = (size_t)1 << b->lg_d;
+    NttPlan* plan = ntt_plan_get(b->lg_d, b->full_rate_bits, false, 7, st);
+    if (!plan) return fail(PCS_ERR_ALLOC, "twiddle table allocation failed");
+    bool contiguous = true;
+    for (size_t j = 0; j < count; j++) {
+        if (!polys[j]) return fail(PCS_ERR_ARG, "NULL polynomial pointer");
+        contiguous = contiguous && polys[j] == polys[0] + j * d;
+    }
+    DevBuf table, staged;
+    const uint64_t* src = polys[0];
+    const uint64_t* const* ptrs = nullptr;
+    if (!contiguous) {
+        if (b->lg_d >= 1) {
+            PCS_CUDA(table.alloc(count * sizeof(uint64_t*), st));
+            PCS_CUDA(cudaMemcpyAsync(table.p, polys, count * sizeof(uint64_t*), cudaMemcpyHostToDevice, st));
+            ptrs = (const uint64_t* const*)table.p;
+        } else {
+            PCS_CUDA(staged.alloc(count * d * 8, st));
+            int rc = stage_polys(polys, count, d, true, staged.u64(), st);
+            if (rc) return rc;
+            src = staged.u64();
+        }
+    }
+    PCS_CUDA(ntt_lde_cosets(plan, src, d, b->lde + poly_first * b->n, b->n, count, b->coset_first, b->rate_bits, st, ptrs));
+    return PCS_OK;   // asynchronous on pcs_stream()
+}
+
+int pcs_shard_finish(pcs_batch* b, uint64_t* cap_out) {
+    if (!b) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (b->committed) return fail(PCS_ERR_ARG, "batch already finished");
+    cudaStream_t st = g_ctx.stream;
+    PCS_CUDA(cudaEventRecord(b->ev[2], st));
+    PCS_CUDA(cudaEventRecord(b->ev[3], st));
+    int rc = build_tree_dev(b->lde, b->n, b->w, b->lg_d + b->rate_bits, b->cap_height, b->digests, b->cap, st, b->ev[4]);
+    if (rc) return rc;
+    PCS_CUDA(cudaEventRecord(b->ev[5], st));
+    b->committed = true;
+    if (cap_out) {
+        PCS_CUDA(cudaMemcpyAsync(cap_out, b->cap, ((size_t)32) << b->cap_height, cudaMemcpyDeviceToHost, st));
+        PCS_CUDA(cudaStreamSynchronize(st));
+    }
+    return PCS_OK;
 }
 
 int pcs_commit_from_values(const uint64_t* const* values, size_t w, unsigned lg_d, unsigned rate_bits,

@@ -30,10 +30,18 @@ from . import _ffi
 from .polynomial import log2_strict, reverse_bits
 
 
+class _null_ctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 class ShardPlan:
     """Who owns what for (w polys, d = 2^lg_d, rate_bits, cap_height) over `world` ranks."""
 
-    def __init__(self, w, lg_d, rate_bits, cap_height, world):
+    def __init__(self, w, lg_d, rate_bits, cap_height, world, chunks=1):
         if world < 1 or world & (world - 1):
             raise ValueError(f"world size must be a power of two, got {world}")
         lg_w = log2_strict(world)
@@ -49,6 +57,10 @@ class ShardPlan:
         self.n_leaves = 1 << (lg_d + rate_bits)
         self.local_leaves = self.n_leaves >> lg_w
         self.w_max = -(-w // world)                           # block distribution of polynomials
+        # streaming exchange: the polynomials are cut into `chunks` contiguous groups and EVERY group is block-
+        # distributed over the ranks, so that group c can be gathered (and extended) while group c+1 is still moving
+        self.chunks = max(1, min(int(chunks), w))
+        self.w_chunk = -(-w // self.chunks)
 
     def coset_first(self, rank):
         return rank << self.lg_cosets
@@ -60,8 +72,31 @@ class ShardPlan:
         return leaf // self.local_leaves
 
     def poly_range(self, rank):
+        """chunks == 1: the contiguous block of polynomials rank `rank` holds."""
         lo = min(rank * self.w_max, self.w)
         return lo, min(lo + self.w_max, self.w)
+
+    def chunk_range(self, c):
+        lo = min(c * self.w_chunk, self.w)
+        return lo, min(lo + self.w_chunk, self.w)
+
+    def chunk_rows(self, c):
+        """rows per rank in the gather of chunk c (padded)"""
+        lo, hi = self.chunk_range(c)
+        return -(-(hi - lo) // self.world)
+
+    def poly_ranges(self, rank):
+        """[(lo, hi)] per chunk: the polynomials rank `rank` holds, in the order of its local rows."""
+        out = []
+        for c in range(self.chunks):
+            lo, hi = self.chunk_range(c)
+            m = self.chunk_rows(c)
+            a = min(lo + rank * m, hi)
+            out.append((a, min(a + m, hi)))
+        return out
+
+    def local_polys(self, rank):
+        return [j for lo, hi in self.poly_ranges(rank) for j in range(lo, hi)]
 
     def local_cap_len(self):
         return 1 << self.local_cap_height
@@ -124,6 +159,24 @@ class CudaShardEngine:
                                                   plan.local_cap_height, None, 0, _ffi.PCS_DEVICE_PTRS, _ffi.ptr(cap), C.byref(h)))
         return h, cap
 
+    def shard_begin(self, plan, rank):
+        h = C.c_void_p()
+        self._order_after_torch()
+        _ffi.check(_ffi.lib().pcs_shard_begin(plan.w, plan.lg_d, plan.rate_bits, plan.coset_first(rank), plan.lg_cosets,
+                                              plan.local_cap_height, C.byref(h)))
+        return h
+
+    def shard_extend(self, handle, poly_first, coeffs, count):
+        """coeffs: torch CUDA int64 tensor [>= count][d] holding polynomials poly_first .. poly_first+count-1"""
+        self._order_after_torch()
+        ptrs = _ffi.dev_ptr_array(coeffs.data_ptr(), count, coeffs.shape[1])
+        _ffi.check(_ffi.lib().pcs_shard_extend(handle, poly_first, count, ptrs))
+
+    def shard_finish(self, handle, plan):
+        cap = np.empty((plan.local_cap_len(), 4), dtype=np.uint64)
+        _ffi.check(_ffi.lib().pcs_shard_finish(handle, _ffi.ptr(cap)))
+        return cap
+
     def two_to_one(self, left, right):
         from .hashing import PoseidonHash
 
@@ -159,6 +212,18 @@ class ShardedPolynomialBatch:
     def __init__(self):
         self._h = None
 
+    _side_streams = {}
+
+    @classmethod
+    def _side_stream(cls, dev):
+        """one copy / collective stream per device, kept for the life of the process"""
+        import torch
+
+        k = str(dev)
+        if k not in cls._side_streams:
+            cls._side_streams[k] = torch.cuda.Stream(device=dev)
+        return cls._side_streams[k]
+
     # ---- peer-memory exchange ---------------------------------------------------------------------------
     _symm_cache = {}
 
@@ -180,12 +245,16 @@ class ShardedPolynomialBatch:
     # ---- constructors (collective: every rank of `group` calls them) ---------------------------------
     @classmethod
     def from_coeffs(cls, local_coeffs, n_polys, rate_bits, cap_height, group=None, engine=None, partitioned=True,
-                    exchange="auto"):
+                    exchange="auto", chunks=1):
         """oracle.rs:68-98 over a process group.
 
         partitioned=True : `local_coeffs` is this rank's block [poly_range(rank)][d] of the n_polys polynomials
                            (torch int64 tensor on the rank's device, bit pattern = u64);
         partitioned=False: every rank already holds all [n_polys][d] coefficients.
+        chunks           : > 1 = streaming exchange (needs partitioned=True): the polynomials are cut into `chunks`
+                           groups, each block-distributed over the ranks (ShardPlan.poly_ranges); `local_coeffs`
+                           holds this rank's rows in chunk order and may live in PINNED HOST memory.  Chunk c+1 is
+                           copied / all-gathered on a side stream while the LDE of chunk c runs.
         exchange         : how the other ranks' coefficient blocks reach this rank's LDE --
             "allgather": NCCL all-gather into a local [W][d] matrix, then the LDE;
             "peer"     : NO collective: every block sits in symmetric memory and the first NTT pass of each rank
@@ -203,9 +272,11 @@ class ShardedPolynomialBatch:
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         engine = engine or CudaShardEngine()
         d = int(local_coeffs.shape[1])
-        plan = ShardPlan(n_polys, log2_strict(d), rate_bits, cap_height, world)
+        plan = ShardPlan(n_polys, log2_strict(d), rate_bits, cap_height, world, chunks if (partitioned and world > 1) else 1)
         if exchange == "auto":
             exchange = "allgather"
+        if plan.chunks > 1:
+            return cls._from_coeffs_streaming(local_coeffs, plan, rank, world, group, engine)
         poly_ptrs = None
         if partitioned and world > 1 and exchange == "peer":
             lo, hi = plan.poly_range(rank)
@@ -258,6 +329,67 @@ class ShardedPolynomialBatch:
         return self
 
     @classmethod
+    def _from_coeffs_streaming(cls, local_coeffs, plan, rank, world, group, engine):
+        """chunked exchange overlapped with the LDE: side stream = (H2D of chunk c) -> all-gather of chunk c;
+        main stream = LDE of chunk c as soon as its gather has landed; then leaf hashing and the subtrees."""
+        import torch
+        import torch.distributed as dist
+
+        d = int(local_coeffs.shape[1])
+        ranges = plan.poly_ranges(rank)
+        if local_coeffs.shape[0] != sum(hi - lo for lo, hi in ranges):
+            raise ValueError(f"rank {rank} must hold polynomials {ranges} ({sum(hi - lo for lo, hi in ranges)} rows), "
+                             f"got {local_coeffs.shape[0]}")
+        cuda = torch.cuda.is_available() and dist.get_backend(group) == "nccl"
+        dev = torch.device("cuda", torch.cuda.current_device()) if cuda else local_coeffs.device
+        main = torch.cuda.current_stream() if cuda else None
+        side = cls._side_stream(dev) if cuda else None
+        if cuda:
+            side.wait_stream(main)
+        gathered, events, row = [], [], 0
+        for c in range(plan.chunks):
+            lo, hi = ranges[c]
+            m = plan.chunk_rows(c)
+            # buffers come from the MAIN stream's allocator pool (reused from commit to commit) and are handed to the
+            # side stream with record_stream
+            mine = torch.zeros((m, d), dtype=torch.int64, device=dev) if hi - lo < m else torch.empty((m, d), dtype=torch.int64, device=dev)
+            g = torch.empty((world * m, d), dtype=torch.int64, device=dev)
+            if cuda:
+                side.wait_stream(main)       # the zero fill above runs on the main stream
+                mine.record_stream(side)
+                g.record_stream(side)
+            with (torch.cuda.stream(side) if cuda else _null_ctx()):
+                mine[: hi - lo].copy_(local_coeffs[row : row + hi - lo], non_blocking=True)
+                dist.all_gather_into_tensor(g, mine, group=group)
+                ev = torch.cuda.Event() if cuda else None
+                if cuda:
+                    ev.record(side)
+            row += hi - lo
+            gathered.append((g, mine))
+            events.append(ev)
+        self = cls()
+        self.plan, self.rank, self.world, self.group, self.engine = plan, rank, world, group, engine
+        self.degree_log, self.rate_bits, self.blinding, self.cap_height = plan.lg_d, plan.rate_bits, False, plan.cap_height
+        self.n_polys = plan.w
+        self._h = engine.shard_begin(plan, rank)
+        for c in range(plan.chunks):
+            clo, chi = plan.chunk_range(c)
+            if cuda:
+                main.wait_event(events[c])
+            engine.shard_extend(self._h, clo, gathered[c][0], chi - clo)
+        local_cap = engine.shard_finish(self._h, plan)
+        self._coeffs = gathered          # keeps the gathered chunks alive ([chunk][world*m][d]); polynomials of chunk c = rows [0, len_c)
+        mine = torch.from_numpy(local_cap.view(np.int64)).to(dev)
+        allc = torch.empty((world * mine.shape[0], 4), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine, group=group)
+        caps = allc.cpu().numpy().view(np.uint64).reshape(world, -1, 4)
+        self._local_caps = caps
+        self.cap = plan.assemble_cap(caps, engine.two_to_one)
+        self.exchange = f"allgather, {plan.chunks} chunks overlapped with the LDE"
+        self._dev = dev
+        return self
+
+    @classmethod
     def from_values(cls, local_values, n_polys, rate_bits, cap_height, group=None, engine=None):
         """oracle.rs:43-65 over a process group: each rank IFFTs its own block of the polynomials
         (values are overwritten by coefficients), then from_coeffs."""
@@ -266,6 +398,10 @@ class ShardedPolynomialBatch:
         return cls.from_coeffs(local_values, n_polys, rate_bits, cap_height, group, engine, partitioned=True)
 
     # ---- accessors ---------------------------------------------------------------------------------
+    def _device(self):
+        d = getattr(self, "_dev", None)
+        return d if d is not None else self._coeffs.device
+
     @property
     def n_local_digests(self):
         return 2 * (self.plan.local_leaves - self.plan.local_cap_len())
@@ -286,7 +422,7 @@ class ShardedPolynomialBatch:
         if mine.any():
             rows[mine] = self.engine.get_rows(self._h, idx[mine] - lo, self.n_polys)
         if self.world > 1:
-            t = torch.from_numpy(rows.view(np.int64)).to(self._coeffs.device)
+            t = torch.from_numpy(rows.view(np.int64)).to(self._device())
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)   # disjoint owners: sum == select
             rows = t.cpu().numpy().view(np.uint64)
         return rows
@@ -311,7 +447,7 @@ class ShardedPolynomialBatch:
             sib[:] = plan.extend_proof(owner, local, self._local_caps.reshape(self.world, -1, 4)[:, 0], self.engine.two_to_one) \
                 if plan.top_levels else local
         if self.world > 1:
-            t = torch.from_numpy(sib.view(np.int64)).to(self._coeffs.device)
+            t = torch.from_numpy(sib.view(np.int64)).to(self._device())
             dist.broadcast(t, src=dist.get_global_rank(self.group, owner) if self.group is not None else owner, group=self.group)
             sib = t.cpu().numpy().view(np.uint64)
         from .hashing import MerkleProof

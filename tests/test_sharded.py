@@ -36,6 +36,25 @@ class OracleShardEngine:
         self.batches[h] = (np.ascontiguousarray(leaves[lo:hi]), digests, plan)
         return h, cap
 
+    def shard_begin(self, plan, rank):
+        h = len(self.batches) + 1
+        self.batches[h] = {"plan": plan, "rank": rank, "coeffs": np.zeros((plan.w, 1 << plan.lg_d), dtype=np.uint64), "seen": 0}
+        return h
+
+    def shard_extend(self, h, poly_first, coeffs, count):
+        b = self.batches[h]
+        b["coeffs"][poly_first : poly_first + count] = self._u64(coeffs)[:count]
+        b["seen"] += count
+
+    def shard_finish(self, h, plan):
+        import torch
+
+        b = self.batches.pop(h)
+        assert b["seen"] == plan.w
+        h2, cap = self.commit_shard(torch.from_numpy(b["coeffs"].view(np.int64)), plan.w, plan, b["rank"])
+        self.batches[h] = self.batches.pop(h2)
+        return cap
+
     def two_to_one(self, l, r):
         return oracle.two_to_one(np.ascontiguousarray(l), np.ascontiguousarray(r))
 
@@ -73,6 +92,24 @@ def test_shard_plan_partitions(w, lg_d, r, cap, world):
     assert p.coset_first(world - 1) + (1 << p.lg_cosets) == 1 << r
     assert p.local_leaves == (1 << lg_d) << p.lg_cosets
     assert (p.local_cap_len() * world) >> p.top_levels == 1 << cap
+
+
+@pytest.mark.parametrize("w,world,chunks", [(135, 8, 4), (135, 2, 3), (20, 8, 4), (7, 4, 2), (5, 2, 9)])
+def test_shard_plan_chunked_distribution(w, world, chunks):
+    from plonky2_demo_b200.sharded import ShardPlan
+
+    p = ShardPlan(w, 4, 3, 0, world, chunks)
+    owned = sorted(j for k in range(world) for j in p.local_polys(k))
+    assert owned == list(range(w))                       # every polynomial exactly once
+    for c in range(p.chunks):
+        lo, hi = p.chunk_range(c)
+        m = p.chunk_rows(c)
+        # gathered chunk = ranks' sub-blocks padded to m rows: valid rows are contiguous from the start
+        got = [j for k in range(world) for j in range(*p.poly_ranges(k)[c])]
+        assert got == list(range(lo, hi))
+        sizes = [p.poly_ranges(k)[c][1] - p.poly_ranges(k)[c][0] for k in range(world)]
+        full = [k for k, sz in enumerate(sizes) if sz == m]
+        assert full == list(range(len(full))) and all(sz <= m for sz in sizes)
 
 
 def test_shard_plan_rejects():
@@ -118,7 +155,7 @@ def test_single_process_shards_assemble_to_reference(w, lg_d, r, cap, world):
 # ---------------------------------------------------------------------------------------------
 # collectives under gloo, world_size 2
 # ---------------------------------------------------------------------------------------------
-def _gloo_worker(rank, world, port, w, lg_d, r, cap, from_values, q):
+def _gloo_worker(rank, world, port, w, lg_d, r, cap, from_values, q, chunks=1):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -132,17 +169,17 @@ def _gloo_worker(rank, world, port, w, lg_d, r, cap, from_values, q):
     try:
         coeffs = seeded_polys(w, 1 << lg_d, base_seed=5)
         ref = oracle.commit_from_coeffs(coeffs, r, cap)
-        plan = ShardPlan(w, lg_d, r, cap, world)
-        lo, hi = plan.poly_range(rank)
+        plan = ShardPlan(w, lg_d, r, cap, world, chunks)
         src = oracle.fft(coeffs) if from_values else coeffs
-        local = torch.from_numpy(np.ascontiguousarray(src[lo:hi]).view(np.int64).copy())
+        local = torch.from_numpy(np.ascontiguousarray(src[plan.local_polys(rank)]).view(np.int64).copy())
         eng = OracleShardEngine()
         if from_values:
             b = ShardedPolynomialBatch.from_values(local, w, r, cap, engine=eng)
         else:
-            b = ShardedPolynomialBatch.from_coeffs(local, w, r, cap, engine=eng)
+            b = ShardedPolynomialBatch.from_coeffs(local, w, r, cap, engine=eng, chunks=chunks)
         ok = np.array_equal(b.cap, ref["cap"])
-        ok &= np.array_equal(b._coeffs.numpy().view(np.uint64)[:w], coeffs)
+        if chunks == 1:
+            ok &= np.array_equal(b._coeffs.numpy().view(np.uint64)[:w], coeffs)
         leaves = [0, plan.local_leaves - 1, plan.local_leaves, plan.n_leaves - 1]
         ok &= np.array_equal(b.get_rows(leaves), ref["leaves"][leaves])
         ok &= np.array_equal(b.get_lde_values(3, 2), ref["leaves"][int(format(6, f"0{lg_d + r}b")[::-1], 2)])
@@ -158,8 +195,8 @@ def _gloo_worker(rank, world, port, w, lg_d, r, cap, from_values, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("w,lg_d,r,cap,from_values", [(9, 5, 3, 4, False), (7, 4, 1, 0, False), (9, 5, 3, 4, True)])
-def test_gloo_world2_sharded_commit(w, lg_d, r, cap, from_values):
+@pytest.mark.parametrize("w,lg_d,r,cap,from_values,chunks", [(9, 5, 3, 4, False, 1), (7, 4, 1, 0, False, 1), (9, 5, 3, 4, True, 1), (9, 5, 3, 4, False, 3)])
+def test_gloo_world2_sharded_commit(w, lg_d, r, cap, from_values, chunks):
     import socket
 
     import torch.multiprocessing as mp
@@ -170,7 +207,7 @@ def test_gloo_world2_sharded_commit(w, lg_d, r, cap, from_values):
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_gloo_worker, args=(k, 2, port, w, lg_d, r, cap, from_values, q)) for k in range(2)]
+    procs = [ctx.Process(target=_gloo_worker, args=(k, 2, port, w, lg_d, r, cap, from_values, q, chunks)) for k in range(2)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in procs)
@@ -207,6 +244,54 @@ def test_cuda_shards_assemble_to_reference(w, lg_d, r, cap, world):
         assert np.array_equal(eng.get_rows(hs[k], idx, w), ref["leaves"][idx + plan.leaf_range(k)[0]])
     for h in hs:
         eng.free(h)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,lg_d,r,cap,world,groups", [(135, 10, 3, 4, 8, [40, 40, 55]), (9, 12, 3, 2, 2, [1, 8]), (20, 13, 2, 0, 4, [7, 6, 7])])
+def test_cuda_streaming_shard_commit(w, lg_d, r, cap, world, groups):
+    """pcs_shard_begin / extend / finish: polynomials supplied in groups (contiguous and scattered device pointers)."""
+    import ctypes as C
+
+    import torch
+
+    import plonky2_demo_b200 as p
+    from plonky2_demo_b200 import _ffi
+    from plonky2_demo_b200.sharded import ShardPlan
+
+    p.init(0)
+    L = _ffi.lib()
+    coeffs = seeded_polys(w, 1 << lg_d, base_seed=17)
+    ref = oracle.commit_from_coeffs(coeffs, r, cap)
+    plan = ShardPlan(w, lg_d, r, cap, world)
+    t = torch.from_numpy(coeffs.view(np.int64).copy()).cuda()
+    scattered = [torch.from_numpy(coeffs[j].view(np.int64).copy()).cuda() for j in range(w)]
+    caps = []
+    for k in range(world):
+        h = C.c_void_p()
+        _ffi.check(L.pcs_shard_begin(w, lg_d, r, plan.coset_first(k), plan.lg_cosets, plan.local_cap_height, C.byref(h)))
+        first = 0
+        for gi, cnt in enumerate(groups):
+            if gi % 2 == 0:
+                ptrs = _ffi.dev_ptr_array(t.data_ptr() + 8 * first * (1 << lg_d), cnt, 1 << lg_d)
+            else:
+                ptrs = (_ffi.u64p * cnt)(*[C.cast(C.c_void_p(scattered[first + i].data_ptr()), _ffi.u64p) for i in range(cnt)])
+            _ffi.check(L.pcs_shard_extend(h, first, cnt, ptrs))
+            first += cnt
+        assert first == w
+        cap_k = np.empty((plan.local_cap_len(), 4), dtype=np.uint64)
+        _ffi.check(L.pcs_shard_finish(h, _ffi.ptr(cap_k)))
+        assert L.pcs_shard_extend(h, 0, 1, _ffi.dev_ptr_array(t.data_ptr(), 1, 1 << lg_d)) != 0   # finished batches are closed
+        caps.append(cap_k)
+        if plan.top_levels == 0:
+            n_dig = 2 * (plan.local_leaves - plan.local_cap_len())
+            dig = np.empty((n_dig, 4), dtype=np.uint64)
+            _ffi.check(L.pcs_batch_digests(h, _ffi.ptr(dig)))
+            per = ref["digests"].shape[0] // world
+            assert np.array_equal(dig, ref["digests"][k * per:(k + 1) * per])
+        L.pcs_batch_free(h)
+    from plonky2_demo_b200.sharded import CudaShardEngine
+
+    assert np.array_equal(plan.assemble_cap(np.stack(caps), CudaShardEngine().two_to_one), ref["cap"])
 
 
 @pytest.mark.gpu

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--cap-height", type=int, default=4)
     ap.add_argument("--samples", type=int, default=3)
     ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer"])
+    ap.add_argument("--chunks", type=int, default=2)
     ap.add_argument("--eval-polys", type=int, default=4, help="polynomials evaluated directly on the CPU per sampled leaf")
     a = ap.parse_args()
 
@@ -51,12 +52,13 @@ def main():
 
     w, lg_d, r, cap_h = a.width, a.lg_d, a.rate_bits, a.cap_height
     d = 1 << lg_d
-    plan = ShardPlan(w, lg_d, r, cap_h, world)
-    lo, hi = plan.poly_range(rank)
+    chunks = 1 if a.exchange == "peer" else a.chunks
+    plan = ShardPlan(w, lg_d, r, cap_h, world, chunks)
+    mine = plan.local_polys(rank)
     t0 = time.perf_counter()
-    host = np.empty((hi - lo, d), dtype=np.uint64)
-    for j in range(hi - lo):
-        host[j] = splitmix64_stream(0x5EED0000 + lo + j, d)
+    host = np.empty((len(mine), d), dtype=np.uint64)
+    for j, pj in enumerate(mine):
+        host[j] = splitmix64_stream(0x5EED0000 + pj, d)
     local_coeffs = torch.from_numpy(host.view(np.int64)).to(dev)
     gen_s = time.perf_counter() - t0
 
@@ -69,7 +71,7 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        batch = ShardedPolynomialBatch.from_coeffs(local_coeffs, w, r, cap_h, partitioned=True, exchange=a.exchange)
+        batch = ShardedPolynomialBatch.from_coeffs(local_coeffs, w, r, cap_h, partitioned=True, exchange=a.exchange, chunks=plan.chunks)
         e1.record(stream)
         dist.barrier()
         torch.cuda.synchronize()
@@ -92,8 +94,8 @@ def main():
     # direct evaluation: each rank checks its own polynomials (first --eval-polys of its block) at every sampled point
     for k, leaf in enumerate(leaves):
         x = 7 * pow(wN, brev(leaf, lg_n), P) % P
-        for j in range(min(a.eval_polys, hi - lo)):
-            ok_rows &= int(rows[k][lo + j]) == oracle.poly_eval(host[j], x)
+        for j in range(min(a.eval_polys, len(mine))):
+            ok_rows &= int(rows[k][mine[j]]) == oracle.poly_eval(host[j], x)
     flag = torch.tensor([int(ok_rows)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
@@ -104,7 +106,7 @@ def main():
             "exchange": batch.exchange,
             "ms": times, "best_ms": best, "elems_per_s": elems / (best * 1e-3), "lde_bytes": elems * 8,
             "sampled_leaves": leaves, "merkle_paths_verify_against_cap": bool(ok_paths),
-            "rows_equal_direct_cpu_evaluation": bool(flag.item()), "polys_evaluated_per_rank": min(a.eval_polys, hi - lo),
+            "rows_equal_direct_cpu_evaluation": bool(flag.item()), "polys_evaluated_per_rank": min(a.eval_polys, len(mine)),
             "input_generation_s": gen_s, "cap0": [hex(int(v)) for v in batch.cap[0]]}))
     batch.free()
     dist.barrier()
