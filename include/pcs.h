@@ -70,6 +70,11 @@ PCS_API int pcs_synchronize(void);
 /* ---- primitives (unit-testable against the reference's own tests) ------------------------------ */
 /* Poseidon::poseidon on n states, in place.                      plonky2/src/hash/poseidon.rs:599-609 */
 PCS_API int pcs_poseidon_permute(uint64_t* states /*[n][12]*/, size_t n);
+/* fri_proof_of_work: smallest witness w in 0..p-1 such that, with w written to lane `witness_pos` of the duplex
+ * intermediate `state` (sponge state overwritten with the pending challenger inputs), the permuted state's last rate
+ * lane has >= min_leading_zeros leading zeros.  The reference searches with rayon find_any (any hit; the smallest one
+ * with a single thread, which is how the demo runs).                plonky2/src/fri/prover.rs:115-160        */
+PCS_API int pcs_pow_grind(const uint64_t* state /*[12]*/, unsigned witness_pos, unsigned min_leading_zeros, uint64_t* witness);
 /* Hasher::hash_or_noop on n rows of `len` elements.               plonky2/src/plonk/config.rs:55-66   */
 PCS_API int pcs_hash_or_noop(const uint64_t* rows /*[n][len]*/, size_t n, size_t len, uint64_t* out /*[n][4]*/);
 /* PoseidonHash::two_to_one = compress.                            plonky2/src/hash/hashing.rs:98-115  */

@@ -18,7 +18,7 @@ every compute call raises PcsError when no CUDA device is present.
 """
 from ._ffi import LIB_PATH, SIGNATURES, PcsError, lib  # noqa: F401
 from .config import CircuitConfig, PoseidonGoldilocksConfig  # noqa: F401
-from .fri import FriConfig, FriParams, FriReductionStrategy, PolynomialBatch, SALT_SIZE  # noqa: F401
+from .fri import FriConfig, FriParams, FriReductionStrategy, PolynomialBatch, SALT_SIZE, fri_proof_of_work  # noqa: F401
 from .hashing import (  # noqa: F401
     HashOut,
     MerkleCap,

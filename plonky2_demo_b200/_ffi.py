@@ -23,6 +23,7 @@ SIGNATURES = {
     "pcs_stream": (C.c_void_p, []),
     "pcs_synchronize": (C.c_int, []),
     "pcs_poseidon_permute": (C.c_int, [u64p, sz]),
+    "pcs_pow_grind": (C.c_int, [u64p, C.c_uint, C.c_uint, u64p]),
     "pcs_hash_or_noop": (C.c_int, [u64p, sz, sz, u64p]),
     "pcs_two_to_one": (C.c_int, [u64p, u64p, sz, u64p]),
     "pcs_ntt": (C.c_int, [u64p, sz, C.c_uint, C.c_int]),

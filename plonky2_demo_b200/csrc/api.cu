@@ -178,6 +178,34 @@ int pcs_poseidon_permute(uint64_t* states, size_t n) {
     return PCS_OK;
 }
 
+int pcs_pow_grind(const uint64_t* state, unsigned witness_pos, unsigned min_leading_zeros, uint64_t* witness) {
+    PCS_NEED_INIT();
+    if (!state || !witness) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (witness_pos >= 12) return fail(PCS_ERR_ARG, "witness position outside the sponge state");
+    if (min_leading_zeros > 40) return fail(PCS_ERR_ARG, "proof-of-work difficulty above 40 bits is not supported");
+    cudaStream_t st = g_ctx.stream;
+    DevBuf d_state, d_best;
+    PCS_CUDA(d_state.alloc(12 * 8, st));
+    PCS_CUDA(d_best.alloc(8, st));
+    PCS_CUDA(cudaMemcpyAsync(d_state.p, state, 12 * 8, cudaMemcpyHostToDevice, st));
+    const uint64_t P = 0xFFFFFFFF00000001ULL, none = ~0ULL;
+    PCS_CUDA(cudaMemcpyAsync(d_best.p, &none, 8, cudaMemcpyHostToDevice, st));
+    // batches sized to the expected number of tries (2^min_lz), at least 2^20 and at most 2^26 candidates
+    uint64_t batch = (uint64_t)1 << (min_leading_zeros < 20 ? 20 : (min_leading_zeros > 26 ? 26 : min_leading_zeros));
+    for (uint64_t base = 0; base < P; base += batch) {          // candidates 0 ..= p - 1 (prover.rs:141)
+        uint64_t n = P - base < batch ? P - base : batch;
+        PCS_CUDA(launch_pow_search(d_state.u64(), witness_pos, min_leading_zeros, base, n, (unsigned long long*)d_best.p, st));
+        uint64_t best;
+        PCS_CUDA(cudaMemcpyAsync(&best, d_best.p, 8, cudaMemcpyDeviceToHost, st));
+        PCS_CUDA(cudaStreamSynchronize(st));
+        if (best != none) {
+            *witness = best;
+            return PCS_OK;
+        }
+    }
+    return fail(PCS_ERR_ARG, "Proof of work failed. This is highly unlikely!");
+}
+
 int pcs_hash_or_noop(const uint64_t* rows, size_t n, size_t len, uint64_t* out) {
     PCS_NEED_INIT();
     if (n == 0) return PCS_OK;

@@ -34,6 +34,9 @@ static inline int ilog2_strict(size_t n) {
 // ------------------------------------------------------------------------------------------------
 // In-place Poseidon permutation of n states, row-major [n][12].
 cudaError_t launch_permute(uint64_t* states, size_t n, cudaStream_t st);
+// FRI proof-of-work: smallest candidate in [base, base + n) whose response has >= min_lz leading zeros -> atomicMin(*best)
+cudaError_t launch_pow_search(const uint64_t* state_dev, unsigned pos, unsigned min_lz, uint64_t base, uint64_t n,
+                              unsigned long long* best_dev, cudaStream_t st);
 // Leaf digests from a column-major (poly-major) matrix: element (leaf i, column j) at
 // cols[j*col_stride + i].  Digest of leaf i goes to its slot in the reference digest layout
 // (merkle_tree.rs:43-51) or into cap when the subtree is a single leaf.

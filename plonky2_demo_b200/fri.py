@@ -109,6 +109,20 @@ class FriParams:
         return 1 << self.final_poly_bits()
 
 
+def fri_proof_of_work(sponge_state, input_buffer, config):
+    """fri/prover.rs:115-160 on the GPU.  `sponge_state`: the challenger's 12-lane state, `input_buffer`: its pending
+    inputs (len < 12, overwritten into the state first, :136-138).  Returns the PoW witness (smallest valid one)."""
+    st = _ffi.as_u64(sponge_state, copy=True).reshape(12)
+    buf = _ffi.as_u64(input_buffer).reshape(-1)
+    if buf.shape[0] >= 12:
+        raise ValueError("input_buffer.len() < WIDTH is an invariant of Challenger")
+    st[: buf.shape[0]] = buf
+    min_leading_zeros = config.proof_of_work_bits + (64 - 64)   # (64 - F::order().bits()) = 0 for Goldilocks, :119
+    w = C.c_uint64()
+    _ffi.check(_ffi.lib().pcs_pow_grind(_ffi.ptr(st), buf.shape[0], min_leading_zeros, C.byref(w)))
+    return int(w.value)
+
+
 class _DeviceLeaves:
     """`merkle_tree.leaves` of a device-resident batch: rows are gathered on demand."""
 

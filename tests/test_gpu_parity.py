@@ -392,3 +392,21 @@ def test_full_size_commit_properties(pcs):
                                                  _ffi.PCS_DEVICE_PTRS, _ffi.ptr(cap2), C.byref(h)))
     _ffi.lib().pcs_batch_free(h)
     assert np.array_equal(cap2, cap_hashes)
+
+
+@pytest.mark.parametrize("bits,buffered", [(8, 3), (12, 0), (16, 7)])
+def test_fri_proof_of_work(pcs, bits, buffered):
+    """fri/prover.rs:115-160: the witness is the smallest candidate whose response has enough leading zeros."""
+    rng = np.random.default_rng(bits)
+    state = rng.integers(0, P, size=12, dtype=np.uint64)
+    buf = rng.integers(0, P, size=buffered, dtype=np.uint64)
+    cfg = pcs.FriConfig(3, 4, bits, pcs.FriReductionStrategy.ConstantArityBits(4, 5), 28)
+    w = pcs.fri_proof_of_work(state, buf, cfg)
+    st = state.copy()
+    st[:buffered] = buf
+    cand = np.arange(0, w + 1, dtype=np.uint64)
+    states = np.tile(st, (cand.size, 1))
+    states[:, buffered] = cand
+    resp = oracle.poseidon(states)[:, 7]
+    ok = resp < np.uint64(1 << (64 - bits))            # >= bits leading zeros
+    assert ok[-1] and not ok[:-1].any(), "not the smallest valid witness"
