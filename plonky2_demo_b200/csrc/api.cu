@@ -459,6 +459,7 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
 
     pcs_batch* b = new pcs_batch();
     b->w = w; b->salt_w = salt_w; b->lg_d = lg_d; b->rate_bits = lg_cosets; b->cap_height = cap_height;
+    b->full_rate_bits = rate_bits; b->coset_first = coset_first;
     b->n = n; b->n_digests = 2 * (n - n_cap); b->has_ifft = from_values;
     struct Guard { pcs_batch* b; bool armed = true; ~Guard() { if (armed) pcs_batch_free(b); } } guard{b};
     for (auto& e : b->ev) PCS_CUDA(cudaEventCreate(&e));
