@@ -109,3 +109,25 @@ def test_host_helpers(golden):
     with pytest.raises(ValueError):
         c.padded(2)
     assert p.GOLDILOCKS_ORDER == golden["kats"]["field"]["order"]
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (CPU arm of the driver's contract): one JSON line with the contract's keys."""
+    import json
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample-lg-d", "8"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
+        assert k in rec, k
+    assert rec["impl"] == "reference" and rec["unit"] == "elems/s" and rec["value"] > 0
+    assert rec["cpu_baseline"]["kind"] == "port" and rec["e2e"]["h2d_bytes_per_step"] == 0
+    # other ranks of a torchrun launch print nothing
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample-lg-d", "8"], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""

@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--samples", type=int, default=3)
     ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer"])
     ap.add_argument("--chunks", type=int, default=2)
+    ap.add_argument("--from-values", action="store_true",
+                    help="start from point values: each rank IFFTs its own polynomials on its GPU (pcs_ntt_dev), then the sharded from_coeffs")
     ap.add_argument("--eval-polys", type=int, default=4, help="polynomials evaluated directly on the CPU per sampled leaf")
     a = ap.parse_args()
 
@@ -59,6 +61,13 @@ def main():
     host = np.empty((len(mine), d), dtype=np.uint64)
     for j, pj in enumerate(mine):
         host[j] = splitmix64_stream(0x5EED0000 + pj, d)
+    if a.from_values:
+        chunks, plan = 1, ShardPlan(w, lg_d, r, cap_h, world, 1)   # from_values uses the plain block distribution
+        mine = plan.local_polys(rank)
+        host = np.empty((len(mine), d), dtype=np.uint64)
+        for j, pj in enumerate(mine):
+            host[j] = splitmix64_stream(0x5EED0000 + pj, d)
+        local_values = torch.from_numpy(oracle.fft(host).view(np.int64)).to(dev)   # values of the SAME polynomials
     local_coeffs = torch.from_numpy(host.view(np.int64)).to(dev)
     gen_s = time.perf_counter() - t0
 
@@ -71,7 +80,10 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        batch = ShardedPolynomialBatch.from_coeffs(local_coeffs, w, r, cap_h, partitioned=True, exchange=a.exchange, chunks=plan.chunks)
+        if a.from_values:
+            batch = ShardedPolynomialBatch.from_values(local_values.clone(), w, r, cap_h)
+        else:
+            batch = ShardedPolynomialBatch.from_coeffs(local_coeffs, w, r, cap_h, partitioned=True, exchange=a.exchange, chunks=plan.chunks)
         e1.record(stream)
         dist.barrier()
         torch.cuda.synchronize()
