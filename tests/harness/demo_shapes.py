@@ -1,5 +1,7 @@
 #!/usr/bin/env python3
-"""BASELINE.json configs[0]/[1]: the commitments of the matmul demo (plonky2/src/bin/matrix_mul.rs) replayed by SHAPE.
+"""Verification harness (test infrastructure: imports the CPU oracle as the checker).
+
+BASELINE.json configs[0]/[1]: the commitments of the matmul demo (plonky2/src/bin/matrix_mul.rs) replayed by SHAPE.
 
 The Rust prover cannot be built in this image, so "prove ms" itself is not measurable here; what this engine replaces
 inside build()+prove() are the PolynomialBatch commits (circuit_builder.rs:1021; plonk/prover.rs:145,212,260) and the
@@ -7,7 +9,7 @@ FRI commit-phase trees (fri/prover.rs:81-87).  For m = 2 (degree 2^3) and m = 64
 seeded polynomials of exactly those shapes through the C ABI with HOST buffers (pinned-free numpy arrays, like the
 Rust Vecs), checks caps against the CPU oracle and prints GPU vs CPU-port wall times (ms, median of 5).
 
-    python tools/demo_shapes.py            # needs a B200
+    python tests/harness/demo_shapes.py            # needs a B200
 """
 import json
 import os
@@ -15,7 +17,7 @@ import statistics
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -1,9 +1,11 @@
 #!/usr/bin/env python3
-"""BASELINE.json configs[4]: one commitment of 135 polys x 2^24, rate_bits 3 (2^27 leaves, 145 GB of LDE rows)
+"""Verification harness (test infrastructure: imports the CPU oracle as the checker).
+
+BASELINE.json configs[4]: one commitment of 135 polys x 2^24, rate_bits 3 (2^27 leaves, 145 GB of LDE rows)
 sharded over the GPUs of one box.  Run under torchrun, one rank per GPU:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 \
-        tools/large_commit_check.py [--lg-d 24] [--width 135]
+        tests/harness/large_commit_check.py [--lg-d 24] [--width 135]
 
 The LDE rows never leave the GPUs.  Parity at this size (the CPU oracle cannot hold 145 GB) is checked the way
 SURVEY 8d prescribes: sampled leaves are fetched with their Merkle paths and (i) the path is verified against the
@@ -15,7 +17,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
