@@ -410,3 +410,30 @@ def test_fri_proof_of_work(pcs, bits, buffered):
     resp = oracle.poseidon(states)[:, 7]
     ok = resp < np.uint64(1 << (64 - bits))            # >= bits leading zeros
     assert ok[-1] and not ok[:-1].any(), "not the smallest valid witness"
+
+
+def test_commit_random_shapes(pcs):
+    """40 seeded random (w, degree, rate_bits, cap_height, blinding, from_values) shapes incl. non-canonical inputs:
+    cap, digests and leaves equal the oracle's (SURVEY 8d edge grid: d in 2^0..2^11, W in 1..139, rate_bits 0..4)."""
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        lg_d = int(rng.integers(0, 12))
+        r = int(rng.integers(0, 5))
+        w = int(rng.choice([1, 2, 3, 4, 5, 8, 9, 17, 33, 135, 139])) if lg_d <= 8 else int(rng.integers(1, 24))
+        cap = int(rng.integers(0, lg_d + r + 1))
+        blinding = bool(rng.integers(0, 2))
+        from_values = bool(rng.integers(0, 2))
+        d, n = 1 << lg_d, 1 << (lg_d + r)
+        x = rng.integers(0, 1 << 64, size=(w, d), dtype=np.uint64)           # non-canonical values allowed
+        salts = rng.integers(0, 1 << 64, size=(4, n), dtype=np.uint64) if blinding else None
+        if from_values:
+            ref = oracle.commit_from_values(x, r, cap, salts=salts)
+            b = pcs.PolynomialBatch.from_values(x, r, blinding, cap, salts=salts)
+        else:
+            ref = oracle.commit_from_coeffs(x, r, cap, salts=salts)
+            b = pcs.PolynomialBatch.from_coeffs(x, r, blinding, cap, salts=salts)
+        tag = (case, w, lg_d, r, cap, blinding, from_values)
+        assert np.array_equal(b.merkle_tree.cap.hashes, ref["cap"]), tag
+        assert np.array_equal(b.merkle_tree.digests, ref["digests"]), tag
+        assert np.array_equal(b.merkle_tree.leaves[:], ref["leaves"]), tag
+        b.free()
