@@ -17,16 +17,18 @@
 //   [c*d, (c+1)*d): no zero padding, no 7^i pass, no transpose, no bit-reversal pass.
 //   The coset shift is absorbed into the twiddles (zero extra multiplies per element).
 //
-// Decomposition: lg d stages are split into passes of <= 10 stages.  A pass handles, per CTA, a
-// tile of R = 2^nb "rows" (the nb index bits it transforms) x C "columns" (index bits below the
-// pass, or different polynomials) staged in shared memory.  Inside a tile every twiddle factors as
+// Decomposition: lg d stages are split into passes of <= 10 stages.  A pass handles, per CTA, tiles of R = 2^nb "rows"
+// (the nb index bits it transforms) x C "columns" (index bits below the pass, and/or different polynomials).  Inside a
+// tile every twiddle factors as
 //       w(i, q) = gamma_i(G) * psi[q],   gamma_{i-1} = gamma_i^2,
-// with G = (coset, high index bits) fixed per tile: one table lookup (Gamma[G]), nb-1 squarings and
-// 2^nb - 1 products per TILE give all twiddles, shared by all C columns.
+// with G = (coset, high index bits) fixed per CTA: one table lookup (Gamma[G]), nb-1 squarings and the products with
+// psi give all twiddles once per CTA, shared by all columns and by every tile the CTA walks.
+// The stages themselves run on REGISTERS (32 values per thread, two rounds of <= 5 stages, one shared-memory exchange
+// in between): see the pass kernel below.
 //
-// Roofline: HBM traffic is 8 B/elem per pass per direction, but a butterfly costs ~30 integer
-// instructions (4 IMAD.WIDE + reduction + add + sub), so the kernel is bound by the integer pipes
-// unless the tile stages are register-blocked; see DESIGN.md.
+// Roofline: HBM traffic is 8 B/elem per pass per direction, but a butterfly costs 37 integer instructions (4 IMAD.WIDE +
+// carry-chain reduction + canonicalisation + add + sub), so the kernel is bound by the integer ALU pipe, not by HBM:
+// 10 butterflies per output element = 370 instructions per 9 algorithmic bytes.
 #include <map>
 #include <tuple>
 #include <vector>
