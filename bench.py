@@ -376,7 +376,10 @@ def run_ours(a):
     }
 
     lg_passes = (lg_d + 9) // 10 if lg_d else 1
-    launches_per_step = lg_passes + 1 + (lg_d + r - cap_h)   # per rank: LDE passes + leaf hashing + node levels
+    # per rank and commit: LDE passes (once per polynomial group of the streaming exchange) + leaf hashing + node levels
+    lde_groups = plan.chunks if world > 1 else 1
+    local_levels = (lg_d + plan.lg_cosets - plan.local_cap_height) if world > 1 else (lg_d + r - cap_h)
+    launches_per_step = lg_passes * lde_groups + 1 + local_levels
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
