@@ -252,6 +252,10 @@ def test_from_coeffs(pcs, w, lg_d, rate_bits, cap_height):
     step = 1 << rate_bits
     for idx in range(min(d, 4)):
         assert np.array_equal(b.get_lde_values(idx, step), lde[:, idx * step])
+    # get_lde_values_packed(index_start, step): `width` consecutive points, one column per point (oracle.rs:137-159)
+    width = min(d, 4)
+    packed = b.get_lde_values_packed(0, step, width)
+    assert np.array_equal(packed, lde[:, [i * step for i in range(width)]])
     b.free()
 
 
