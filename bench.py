@@ -317,6 +317,22 @@ def run_ours(a):
     ms_per_step = ms_total / a.steps
     value = elems * a.steps / (ms_total * 1e-3)   # one commitment of W*N elements per step, whatever the GPU count
 
+    # ---- BASELINE configs[2]: the batched coset LDE alone, device resident (single GPU) ----
+    lde_alone = None
+    if world == 1:
+        lde_out = torch.empty((w, n), dtype=torch.int64, device=dev)
+        for _ in range(3):
+            _ffi.check(L.pcs_coset_lde_dev(dev_ptrs, w, lg_d, r, 7, C.c_void_p(lde_out.data_ptr())))
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        g0.record(stream)
+        for _ in range(a.steps):
+            _ffi.check(L.pcs_coset_lde_dev(dev_ptrs, w, lg_d, r, 7, C.c_void_p(lde_out.data_ptr())))
+        g1.record(stream)
+        torch.cuda.synchronize()
+        lde_alone = g0.elapsed_time(g1) / a.steps
+        del lde_out
+
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
     e2e = None
     if not a.no_e2e:
@@ -368,6 +384,11 @@ def run_ours(a):
                 "clk_per_permutation_per_sm_lane": (leaf_ms * 1e-3) * sm_mhz * 1e6 * 148 / max(n_perm_leaf, 1),
                 "sm_mhz_used": sm_mhz}
     kernels = {
+        "lde_standalone": None if lde_alone is None else {
+            "workload": f"standalone batched coset LDE: {w} polys x 2^{lg_d}, rate_bits {r} (pcs_coset_lde_dev, 2 launches)",
+            "ms": lde_alone, "elems_per_s": w * n / (lde_alone * 1e-3), "algorithmic_bytes": lde_bytes,
+            "GBps": lde_bytes / (lde_alone * 1e-3) / 1e9, "frac_hbm": lde_bytes / (lde_alone * 1e-3) / 1e9 / peak,
+            "note": "ALU-pipe bound (64-bit modular butterflies), see profiles/r01_ntt_v3.md"},
         "lde": {"ms": lde_ms, "algorithmic_bytes": lde_bytes, "GBps": lde_bytes / (lde_ms * 1e-3) / 1e9, "frac_hbm": lde_bytes / (lde_ms * 1e-3) / 1e9 / peak},
         "leaf_hash": {"ms": leaf_ms, "algorithmic_bytes": leaf_bytes, "GBps": roofline["achieved"], "frac_hbm": roofline["frac"], "permutations": n_perm_leaf},
         "node_levels": {"ms": node_ms, "algorithmic_bytes": node_bytes, "GBps": node_bytes / (node_ms * 1e-3) / 1e9, "permutations": n_perm_node},

@@ -95,6 +95,11 @@ PCS_API int pcs_ntt_dev(uint64_t* polys_dev, size_t w, unsigned lg_n, int invers
  * layout 1: out[N][w] leaf order (== transpose + reverse_index_bits_in_place, oracle.rs:83-84).       */
 PCS_API int pcs_coset_lde(const uint64_t* const* coeffs /*w pointers, d elements each*/, size_t w, unsigned lg_d,
                   unsigned rate_bits, uint64_t shift, uint64_t* out, int layout);
+/* The same LDE entirely on the device (BASELINE configs[2], "standalone batched coset LDE"): w DEVICE pointers to d
+ * coefficients each -> out_dev [w][N] poly-major in LEAF order (coset block c = evaluations on shift*w_N^brev(c)*<w_d>
+ * in bit-reversed order at [c*d, (c+1)*d)), asynchronous on pcs_stream().                              */
+PCS_API int pcs_coset_lde_dev(const uint64_t* const* coeffs_dev, size_t w, unsigned lg_d, unsigned rate_bits,
+                      uint64_t shift, uint64_t* out_dev);
 /* MerkleTree::new(leaves, cap_height).                            plonky2/src/hash/merkle_tree.rs:135-166
  * leaves row-major [n][len]; digests [2(n - 2^cap_height)][4] in the reference's interleaved layout
  * (merkle_tree.rs:43-51); cap [2^cap_height][4].                                                      */

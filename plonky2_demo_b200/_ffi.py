@@ -30,6 +30,7 @@ SIGNATURES = {
     "pcs_coset_intt": (C.c_int, [u64p, sz, C.c_uint, C.c_uint64]),
     "pcs_ntt_dev": (C.c_int, [C.c_void_p, sz, C.c_uint, C.c_int]),
     "pcs_coset_lde": (C.c_int, [u64pp, sz, C.c_uint, C.c_uint, C.c_uint64, u64p, C.c_int]),
+    "pcs_coset_lde_dev": (C.c_int, [u64pp, sz, C.c_uint, C.c_uint, C.c_uint64, C.c_void_p]),
     "pcs_merkle_build": (C.c_int, [u64p, sz, sz, C.c_uint, u64p, u64p]),
     "pcs_commit_from_coeffs": (C.c_int, [u64pp, sz, C.c_uint, C.c_uint, C.c_uint, u64pp, sz, C.c_uint, u64p, C.POINTER(C.c_void_p)]),
     "pcs_commit_shard_from_coeffs": (C.c_int, [u64pp, sz, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, u64pp, sz, C.c_uint, u64p, C.POINTER(C.c_void_p)]),

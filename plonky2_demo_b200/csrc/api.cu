@@ -365,6 +365,40 @@ int pcs_coset_lde(const uint64_t* const* coeffs, size_t w, unsigned lg_d, unsign
     return PCS_OK;
 }
 
+int pcs_coset_lde_dev(const uint64_t* const* coeffs_dev, size_t w, unsigned lg_d, unsigned rate_bits, uint64_t shift,
+                      uint64_t* out_dev) {
+    PCS_NEED_INIT();
+    if (w == 0) return fail(PCS_ERR_ARG, "empty batch (oracle.rs:103 polynomials[0])");
+    if (!coeffs_dev || !out_dev) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (lg_d + rate_bits > 32) return fail(PCS_ERR_TWO_ADICITY, "n_log <= TWO_ADICITY violated");
+    cudaStream_t st = g_ctx.stream;
+    const size_t d = (size_t)1 << lg_d, n = d << rate_bits;
+    NttPlan* plan = ntt_plan_get(lg_d, rate_bits, false, shift, st);
+    if (!plan) return fail(PCS_ERR_ALLOC, "twiddle table allocation failed");
+    bool contiguous = true;
+    for (size_t j = 0; j < w; j++) {
+        if (!coeffs_dev[j]) return fail(PCS_ERR_ARG, "NULL polynomial pointer");
+        contiguous = contiguous && coeffs_dev[j] == coeffs_dev[0] + j * d;
+    }
+    DevBuf table, staged;
+    const uint64_t* src = coeffs_dev[0];
+    const uint64_t* const* ptrs = nullptr;
+    if (!contiguous) {
+        if (lg_d >= 1) {
+            PCS_CUDA(table.alloc(w * sizeof(uint64_t*), st));
+            PCS_CUDA(cudaMemcpyAsync(table.p, coeffs_dev, w * sizeof(uint64_t*), cudaMemcpyHostToDevice, st));
+            ptrs = (const uint64_t* const*)table.p;
+        } else {
+            PCS_CUDA(staged.alloc(w * d * 8, st));
+            int rc = stage_polys(coeffs_dev, w, d, true, staged.u64(), st);
+            if (rc) return rc;
+            src = staged.u64();
+        }
+    }
+    PCS_CUDA(ntt_lde_cosets(plan, src, d, out_dev, n, w, 0, rate_bits, st, ptrs));
+    return PCS_OK;   // asynchronous on pcs_stream()
+}
+
 // leaf digests + all node levels; cols = [width][n] poly-major
 static int build_tree_dev(const uint64_t* cols, size_t n, size_t width, unsigned lg_n, unsigned cap_height,
                           uint64_t* digests, uint64_t* cap, cudaStream_t st, cudaEvent_t after_leaves) {

@@ -441,3 +441,28 @@ def test_commit_random_shapes(pcs):
         assert np.array_equal(b.merkle_tree.digests, ref["digests"]), tag
         assert np.array_equal(b.merkle_tree.leaves[:], ref["leaves"]), tag
         b.free()
+
+
+def test_coset_lde_dev_is_the_leaf_order_lde(pcs):
+    """pcs_coset_lde_dev (BASELINE configs[2]): device in, device out, leaf order; contiguous and scattered inputs."""
+    import ctypes as C
+
+    import torch
+
+    from plonky2_demo_b200 import _ffi
+
+    for w, lg_d, r in [(9, 11, 3), (135, 6, 3), (3, 14, 1), (4, 0, 2)]:
+        d, n = 1 << lg_d, 1 << (lg_d + r)
+        coeffs = seeded_polys(w, d, base_seed=7 * lg_d)
+        ref = oracle.transpose_bitrev(oracle.coset_lde(coeffs, r)).T          # [w][N] in leaf order
+        t = torch.from_numpy(coeffs.view(np.int64).copy()).cuda()
+        out = torch.empty((w, n), dtype=torch.int64, device="cuda")
+        _ffi.check(_ffi.lib().pcs_coset_lde_dev(_ffi.dev_ptr_array(t.data_ptr(), w, d), w, lg_d, r, 7, C.c_void_p(out.data_ptr())))
+        pcs.synchronize()
+        assert np.array_equal(out.cpu().numpy().view(np.uint64), ref)
+        rows = [torch.from_numpy(coeffs[j].view(np.int64).copy()).cuda() for j in range(w)]
+        ptrs = (_ffi.u64p * w)(*[C.cast(C.c_void_p(x.data_ptr()), _ffi.u64p) for x in rows])
+        out.zero_()
+        _ffi.check(_ffi.lib().pcs_coset_lde_dev(ptrs, w, lg_d, r, 7, C.c_void_p(out.data_ptr())))
+        pcs.synchronize()
+        assert np.array_equal(out.cpu().numpy().view(np.uint64), ref)
