@@ -181,6 +181,52 @@ PCS_API void pcs_batch_free(pcs_batch* b);
  * commit reuses its HBM) and still read per-kernel times afterwards.  Synchronises the stream. */
 PCS_API int pcs_timing_totals(float ms[5], unsigned* n_commits, int reset);
 
+/* ---- FRI opening proof on the device: the consumers of a committed batch's coefficients ------------
+ * Extension elements are F::Extension = QuadraticExtension<GoldilocksField> = [u64; 2] = a + b*X, X^2 = 7
+ * (field/src/goldilocks_extensions.rs:14-28); Vec<F::Extension> == flat u64[2n], the layout every ext pointer below uses.
+ * All of these need batches committed with PCS_KEEP_COEFFS (or from_values): the reference keeps `polynomials` too.   */
+
+/* OpeningSet::new's eval_commitment(z, c): c.polynomials[j].to_extension().eval(z) for every j.
+ *                                                                  plonky2/src/plonk/proof.rs:316-322          */
+PCS_API int pcs_batch_eval_ext(const pcs_batch* b, const uint64_t point[2], uint64_t* out /*[w][2]*/);
+
+/* Device-resident PolynomialCoeffs<F::Extension> (coefficients of the polynomial FRI runs on).                       */
+typedef struct pcs_ext_poly pcs_ext_poly;
+PCS_API int pcs_ext_poly_new(const uint64_t* coeffs /*[len][2]*/, size_t len, pcs_ext_poly** out);
+PCS_API int pcs_ext_poly_len(const pcs_ext_poly* p, size_t* len);
+PCS_API int pcs_ext_poly_read(const pcs_ext_poly* p, uint64_t* coeffs /*[len][2]*/);
+PCS_API void pcs_ext_poly_free(pcs_ext_poly* p);
+
+/* The final polynomial of PolynomialBatch::prove_openings (plonky2/src/fri/oracle.rs:171-200), for an instance of
+ * n_batches FriBatchInfo {point, polynomials}: per batch  F_i = sum_j alpha^j f_ij  (ReducingFactor::reduce_polys_base,
+ * util/reducing.rs:84-96),  Q_i = F_i.divide_by_linear(point_i) padded back to d coefficients
+ * (field/src/polynomial/division.rs:75-88),  final = final * alpha^{|batch i|} + Q_i  (shift_poly, reducing.rs:104-107).
+ *   oracles        : the committed batches the instance indexes (all of the same degree, coefficients kept)
+ *   batch_len[i]   : number of polynomials of batch i (>= 1); their (oracle_index, poly_index) pairs follow each other in
+ *                    the two index arrays, batch after batch (FriPolynomialInfo, fri/structure.rs)
+ * Result: d = 2^lg_d coefficients (before .lde(rate_bits)).                                                            */
+PCS_API int pcs_fri_final_poly(const pcs_batch* const* oracles, size_t n_oracles, size_t n_batches,
+                       const uint64_t* points /*[n_batches][2]*/, const size_t* batch_len,
+                       const uint32_t* oracle_index, const uint32_t* poly_index, const uint64_t alpha[2],
+                       pcs_ext_poly** out);
+
+/* p.lde(rate_bits).coset_fft(shift.into()) of an extension polynomial: values in natural order, [len << rate_bits][2]
+ * (`lde_final_values`, oracle.rs:202-207; the transform is F-linear, so it is the base-field coset LDE of both
+ * components -- the extension's root of unity of order <= 2^32 is the base field's, quadratic.rs:70-74).          */
+PCS_API int pcs_ext_coset_lde(const pcs_ext_poly* p, unsigned rate_bits, uint64_t shift, uint64_t* values);
+
+/* One round of fri_committed_trees (plonky2/src/fri/prover.rs:81-87): values = p.lde(rate_bits).coset_fft(shift),
+ * reverse_index_bits_in_place, chunks of 2^arity_bits flattened to leaves of 2 * 2^arity_bits base elements,
+ * MerkleTree::new(leaves, cap_height).  The tree comes back as a batch handle (leaf_len = 2 << arity_bits), so
+ * pcs_batch_get_rows / pcs_batch_prove serve the query phase (prover.rs:183-216).
+ *   shift : 7^(product of the earlier rounds' arities) (prover.rs:77,102).                                          */
+PCS_API int pcs_fri_commit_layer(const pcs_ext_poly* p, unsigned rate_bits, uint64_t shift, unsigned arity_bits,
+                         unsigned cap_height, uint64_t* cap_out /*NULL or [2^cap_height][4]*/, pcs_batch** tree);
+
+/* The fold between two rounds (prover.rs:93-101), in place: coeffs[i] <- reduce_with_powers(coeffs[i*arity ..
+ * (i+1)*arity], beta) = sum_j beta^j coeffs[i*arity + j] (plonk_common.rs:116-128); len /= 2^arity_bits.            */
+PCS_API int pcs_fri_fold(pcs_ext_poly* p, unsigned arity_bits, const uint64_t beta[2]);
+
 #ifdef __cplusplus
 }
 #endif

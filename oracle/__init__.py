@@ -26,7 +26,7 @@ def build(force=False):
     """Compile liboracle.so with the committed Makefile (gcc, OpenMP)."""
     if force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
-        for f in ("oracle.c", "gl64.h", "poseidon_constants.h", "Makefile")
+        for f in ("oracle.c", "fri.c", "gl64.h", "poseidon_constants.h", "Makefile")
     ):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH

@@ -525,3 +525,6 @@ API int ref_num_threads(void) {
     return 1;
 #endif
 }
+
+/* FRI opening proof arithmetic */
+#include "fri.c"

@@ -9,7 +9,9 @@ Names, argument meaning and error behaviour follow the reference:
     PoseidonHash / PoseidonPermutation    plonky2/src/hash/poseidon.rs:637-719
     MerkleTree / MerkleCap / MerkleProof  plonky2/src/hash/merkle_tree.rs:18,39 ; merkle_proofs.rs:17
     FriConfig / FriParams                 plonky2/src/fri/mod.rs:19-103
-    PolynomialBatch                       plonky2/src/fri/oracle.rs:30-159
+    PolynomialBatch                       plonky2/src/fri/oracle.rs:30-159 (+ prove_openings :162-219)
+    Challenger                            plonky2/src/iop/challenger.rs:16-160
+    FriInstanceInfo / FriProof            plonky2/src/fri/structure.rs, fri/proof.rs
     PoseidonGoldilocksConfig              plonky2/src/plonk/config.rs:101-108
 
 All arithmetic runs in hand-written CUDA kernels (libpcs.so).  There is no CPU fallback: importing
@@ -19,6 +21,17 @@ every compute call raises PcsError when no CUDA device is present.
 from ._ffi import LIB_PATH, SIGNATURES, PcsError, lib  # noqa: F401
 from .config import CircuitConfig, PoseidonGoldilocksConfig  # noqa: F401
 from .fri import FriConfig, FriParams, FriReductionStrategy, PolynomialBatch, SALT_SIZE, fri_proof_of_work  # noqa: F401
+from .fri_prover import (  # noqa: F401
+    Challenger,
+    ExtensionPolynomial,
+    FriBatchInfo,
+    FriInstanceInfo,
+    FriOracleInfo,
+    FriPolynomialInfo,
+    FriProof,
+    eval_commitment,
+    prove_openings,
+)
 from .hashing import (  # noqa: F401
     HashOut,
     MerkleCap,
@@ -44,5 +57,6 @@ __all__ = [
     "PolynomialBatch", "PolynomialValues", "PolynomialCoeffs", "MerkleTree", "MerkleCap", "MerkleProof",
     "FriConfig", "FriParams", "FriReductionStrategy", "PoseidonGoldilocksConfig", "PoseidonHash",
     "PoseidonPermutation", "HashOut", "CircuitConfig", "fft_with_options", "ifft_with_options",
-    "verify_merkle_proof_to_cap", "init", "shutdown", "synchronize", "PcsError",
+    "verify_merkle_proof_to_cap", "Challenger", "FriInstanceInfo", "FriBatchInfo", "FriPolynomialInfo", "FriOracleInfo",
+    "FriProof", "ExtensionPolynomial", "eval_commitment", "prove_openings", "init", "shutdown", "synchronize", "PcsError",
 ]

@@ -52,6 +52,17 @@ SIGNATURES = {
     "pcs_batch_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "pcs_batch_free": (None, [C.c_void_p]),
     "pcs_timing_totals": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_uint), C.c_int]),
+    # FRI opening proof
+    "pcs_batch_eval_ext": (C.c_int, [C.c_void_p, u64p, u64p]),
+    "pcs_ext_poly_new": (C.c_int, [u64p, sz, C.POINTER(C.c_void_p)]),
+    "pcs_ext_poly_len": (C.c_int, [C.c_void_p, C.POINTER(sz)]),
+    "pcs_ext_poly_read": (C.c_int, [C.c_void_p, u64p]),
+    "pcs_ext_poly_free": (None, [C.c_void_p]),
+    "pcs_fri_final_poly": (C.c_int, [C.POINTER(C.c_void_p), sz, sz, u64p, C.POINTER(sz), C.POINTER(C.c_uint32),
+                                     C.POINTER(C.c_uint32), u64p, C.POINTER(C.c_void_p)]),
+    "pcs_ext_coset_lde": (C.c_int, [C.c_void_p, C.c_uint, C.c_uint64, u64p]),
+    "pcs_fri_commit_layer": (C.c_int, [C.c_void_p, C.c_uint, C.c_uint64, C.c_uint, C.c_uint, u64p, C.POINTER(C.c_void_p)]),
+    "pcs_fri_fold": (C.c_int, [C.c_void_p, C.c_uint, u64p]),
 }
 
 _lib = None

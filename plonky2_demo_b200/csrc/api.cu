@@ -49,7 +49,7 @@ static void drain_pending() {
     cudaGetLastError();
 }
 
-static int fail(int code, const std::string& msg) {
+int fail(int code, const std::string& msg) {
     set_error(msg);
     return code;
 }
@@ -62,40 +62,20 @@ static int fail(int code, const std::string& msg) {
         }                                                                          \
     } while (0)
 
-// stream-ordered temporary buffer
-struct DevBuf {
-    void* p = nullptr;
-    cudaStream_t st = nullptr;
-    cudaError_t alloc(size_t bytes, cudaStream_t s) {
-        st = s;
-        return cudaMallocAsync(&p, bytes ? bytes : 8, s);
-    }
-    uint64_t* u64() { return (uint64_t*)p; }
-    void release() {
-        if (p) cudaFreeAsync(p, st);
-        p = nullptr;
-    }
-    ~DevBuf() { release(); }
-};
+// leaf digests + all node levels; cols = [width][n] poly-major
+int build_tree_dev(const uint64_t* cols, size_t n, size_t width, unsigned lg_n, unsigned cap_height,
+                          uint64_t* digests, uint64_t* cap, cudaStream_t st, cudaEvent_t after_leaves) {
+    unsigned lg_sub = lg_n - cap_height;
+    PCS_CUDA(launch_leaf_hash_cols(cols, n, (uint32_t)width, n, lg_sub, digests, cap, st));
+    if (after_leaves) PCS_CUDA(cudaEventRecord(after_leaves, st));
+    for (unsigned level = 1; level <= lg_sub; level++)
+        PCS_CUDA(launch_node_level(digests, cap, lg_sub, level, n >> level, st));
+    return PCS_OK;
+}
 
 }  // namespace pcs
 
 using namespace pcs;
-
-struct pcs_batch {
-    size_t w = 0, salt_w = 0;
-    unsigned lg_d = 0, rate_bits = 0, cap_height = 0;   // rate_bits = log2(coset blocks held) for a shard
-    unsigned full_rate_bits = 0, coset_first = 0;       // the LDE this batch is (a shard of)
-    size_t n = 0;          // N = d << rate_bits
-    size_t n_digests = 0;  // 2 (N - 2^cap)
-    uint64_t* coeffs = nullptr;   // [w][d] or null
-    uint64_t* lde = nullptr;      // [w + salt_w][N], leaf order
-    uint64_t* digests = nullptr;  // [n_digests][4]
-    uint64_t* cap = nullptr;      // [2^cap][4]
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool has_ifft = false;
-    bool committed = false;  // all six events recorded
-};
 
 extern "C" {
 
@@ -397,17 +377,6 @@ int pcs_coset_lde_dev(const uint64_t* const* coeffs_dev, size_t w, unsigned lg_d
     }
     PCS_CUDA(ntt_lde_cosets(plan, src, d, out_dev, n, w, 0, rate_bits, st, ptrs));
     return PCS_OK;   // asynchronous on pcs_stream()
-}
-
-// leaf digests + all node levels; cols = [width][n] poly-major
-static int build_tree_dev(const uint64_t* cols, size_t n, size_t width, unsigned lg_n, unsigned cap_height,
-                          uint64_t* digests, uint64_t* cap, cudaStream_t st, cudaEvent_t after_leaves) {
-    unsigned lg_sub = lg_n - cap_height;
-    PCS_CUDA(launch_leaf_hash_cols(cols, n, (uint32_t)width, n, lg_sub, digests, cap, st));
-    if (after_leaves) PCS_CUDA(cudaEventRecord(after_leaves, st));
-    for (unsigned level = 1; level <= lg_sub; level++)
-        PCS_CUDA(launch_node_level(digests, cap, lg_sub, level, n >> level, st));
-    return PCS_OK;
 }
 
 int pcs_merkle_build(const uint64_t* leaves, size_t n, size_t len, unsigned cap_height, uint64_t* digests,

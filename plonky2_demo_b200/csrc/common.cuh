@@ -8,6 +8,22 @@
 
 #include "pcs.h"
 
+// Device-resident PolynomialBatch / MerkleTree (opaque in pcs.h)
+struct pcs_batch {
+    size_t w = 0, salt_w = 0;
+    unsigned lg_d = 0, rate_bits = 0, cap_height = 0;   // rate_bits = log2(coset blocks held) for a shard
+    unsigned full_rate_bits = 0, coset_first = 0;       // the LDE this batch is (a shard of)
+    size_t n = 0;          // N = d << rate_bits
+    size_t n_digests = 0;  // 2 (N - 2^cap)
+    uint64_t* coeffs = nullptr;   // [w][d] or null
+    uint64_t* lde = nullptr;      // [w + salt_w][N], leaf order
+    uint64_t* digests = nullptr;  // [n_digests][4]
+    uint64_t* cap = nullptr;      // [2^cap][4]
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool has_ifft = false;
+    bool committed = false;  // all six events recorded
+};
+
 namespace pcs {
 
 void set_error(const std::string& msg);
@@ -21,6 +37,29 @@ void set_error(const std::string& msg);
         }                                                                                    \
     } while (0)
 
+
+
+int fail(int code, const std::string& msg);   // set_error + return code
+
+// stream-ordered temporary buffer
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    cudaError_t alloc(size_t bytes, cudaStream_t s) {
+        st = s;
+        return cudaMallocAsync(&p, bytes ? bytes : 8, s);
+    }
+    uint64_t* u64() { return (uint64_t*)p; }
+    void release() {
+        if (p) cudaFreeAsync(p, st);
+        p = nullptr;
+    }
+    ~DevBuf() { release(); }
+};
+
+// leaf digests + all node levels of MerkleTree::new over a poly-major matrix cols [width][n] (api.cu)
+int build_tree_dev(const uint64_t* cols, size_t n, size_t width, unsigned lg_n, unsigned cap_height, uint64_t* digests,
+                   uint64_t* cap, cudaStream_t st, cudaEvent_t after_leaves);
 
 static inline int ilog2_strict(size_t n) {
     if (n == 0 || (n & (n - 1))) return -1;

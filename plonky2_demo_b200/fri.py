@@ -187,9 +187,12 @@ class PolynomialBatch:
         return cls._commit(values, True, rate_bits, blinding, cap_height, timing, salts)
 
     @classmethod
-    def from_coeffs(cls, polynomials, rate_bits, blinding, cap_height, timing=None, fft_root_table=None, salts=None):
-        """oracle.rs:68-98"""
-        return cls._commit(polynomials, False, rate_bits, blinding, cap_height, timing, salts)
+    def from_coeffs(cls, polynomials, rate_bits, blinding, cap_height, timing=None, fft_root_table=None, salts=None,
+                    keep_coeffs=False):
+        """oracle.rs:68-98.  keep_coeffs: also keep `polynomials` on the device (PCS_KEEP_COEFFS), which the opening
+        proof (fri_prover.prove_openings, eval_commitment) reads; the host copy the caller passed stays referenced
+        either way."""
+        return cls._commit(polynomials, False, rate_bits, blinding, cap_height, timing, salts, keep_coeffs)
 
     @classmethod
     def _rows(cls, polys):
@@ -203,7 +206,7 @@ class PolynomialBatch:
         return rows
 
     @classmethod
-    def _commit(cls, polys, is_values, rate_bits, blinding, cap_height, timing, salts):
+    def _commit(cls, polys, is_values, rate_bits, blinding, cap_height, timing, salts, keep_coeffs=False):
         rows = cls._rows(polys)
         if len(rows) == 0:
             raise IndexError("index out of bounds: the len is 0 but the index is 0")  # oracle.rs:76 polynomials[0]
@@ -238,7 +241,7 @@ class PolynomialBatch:
             self._coeffs_host = None
         else:
             rc = L.pcs_commit_from_coeffs(pp, len(rows), lg_d, rate_bits, cap_height, sp, len(salt_rows),
-                                          0, _ffi.ptr(cap), C.byref(h))
+                                          _ffi.PCS_KEEP_COEFFS if keep_coeffs else 0, _ffi.ptr(cap), C.byref(h))
             self._coeffs_host = rows
         if rc == _ffi_cap_height_code():
             raise ValueError(L.pcs_last_error().decode())  # merkle_tree.rs:136-142 message

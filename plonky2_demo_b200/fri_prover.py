@@ -1,0 +1,311 @@
+"""FRI opening proof: mirror of plonky2/src/fri/{prover,structure,proof}.rs, iop/challenger.rs and
+PolynomialBatch::prove_openings (fri/oracle.rs:162-219), executed by the CUDA engine.
+
+Everything that touches polynomial data runs on the device and stays there: the openings (eval_commitment), the
+alpha-combination / quotients of prove_openings, the extension-field coset LDE, every commit-phase Merkle tree, the
+folds, the proof-of-work search and the query-phase row / path gathers.  The host keeps the transcript (Challenger,
+a 12-element sponge whose permutation is the engine's Poseidon kernel) and the few hundred field elements of the proof.
+
+Extension elements (F::Extension, D = 2) are pairs (a, b) = a + b X, X^2 = 7; arrays of them are uint64 [n][2].
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Tuple
+
+import numpy as np
+
+from . import _ffi
+from .fri import FriParams, PolynomialBatch, _DeviceMerkleTree, fri_proof_of_work
+from .hashing import MerkleCap, MerkleProof, PoseidonPermutation
+from .polynomial import GOLDILOCKS_ORDER, log2_strict
+
+P = GOLDILOCKS_ORDER
+COSET_SHIFT = 7   # F::coset_shift() = MULTIPLICATIVE_GROUP_GENERATOR (types.rs:437, goldilocks_field.rs:76)
+POWER_OF_TWO_GENERATOR = 1753635133440165772   # goldilocks_field.rs:84
+
+
+def primitive_root_of_unity(n_log):
+    """types.rs:268-272"""
+    assert n_log <= 32
+    g = POWER_OF_TWO_GENERATOR
+    for _ in range(n_log, 32):
+        g = g * g % P
+    return g
+
+
+def ext_mul(x, y):
+    """quadratic.rs:184-192 (host scalars: challenges and opening points only)"""
+    return ((x[0] * y[0] + 7 * x[1] * y[1]) % P, (x[0] * y[1] + x[1] * y[0]) % P)
+
+
+def _ext_arg(x):
+    return (C.c_uint64 * 2)(int(x[0]) % P, int(x[1]) % P)
+
+
+# ---- transcript ---------------------------------------------------------------------------------------------------
+class Challenger:
+    """iop/challenger.rs:16-160: duplex sponge in overwrite mode over the engine's Poseidon permutation."""
+
+    def __init__(self):
+        self.sponge_state = PoseidonPermutation()
+        self.input_buffer: List[int] = []
+        self.output_buffer: List[int] = []
+
+    def observe_element(self, element):
+        self.output_buffer = []
+        self.input_buffer.append(int(element) % P)
+        if len(self.input_buffer) == PoseidonPermutation.RATE:
+            self.duplexing()
+
+    def observe_elements(self, elements):
+        for e in elements:
+            self.observe_element(e)
+
+    def observe_extension_element(self, element):
+        self.observe_elements([element[0], element[1]])
+
+    def observe_extension_elements(self, elements):
+        for e in elements:
+            self.observe_extension_element(e)
+
+    def observe_hash(self, h):
+        self.observe_elements(getattr(h, "elements", h))
+
+    def observe_cap(self, cap):
+        hashes = cap.hashes if isinstance(cap, MerkleCap) else np.asarray(cap).reshape(-1, 4)
+        for h in hashes:
+            self.observe_hash(h)
+
+    def get_challenge(self):
+        if self.input_buffer or not self.output_buffer:
+            self.duplexing()
+        return self.output_buffer.pop()
+
+    def get_n_challenges(self, n):
+        return [self.get_challenge() for _ in range(n)]
+
+    def get_extension_challenge(self):
+        a, b = self.get_n_challenges(2)
+        return (a, b)
+
+    def duplexing(self):
+        assert len(self.input_buffer) <= PoseidonPermutation.RATE
+        self.sponge_state.set_from_iter(self.input_buffer, 0)
+        self.input_buffer = []
+        self.sponge_state.permute()
+        self.output_buffer = [int(x) for x in self.sponge_state.squeeze()]
+
+    def clone(self):
+        c = Challenger()
+        c.sponge_state.state = self.sponge_state.state.copy()
+        c.input_buffer = list(self.input_buffer)
+        c.output_buffer = list(self.output_buffer)
+        return c
+
+
+# ---- instance description (fri/structure.rs) ----------------------------------------------------------------------
+@dataclass
+class FriPolynomialInfo:
+    oracle_index: int
+    polynomial_index: int
+
+    @staticmethod
+    def from_range(oracle_index, polynomial_indices):
+        return [FriPolynomialInfo(oracle_index, j) for j in polynomial_indices]
+
+
+@dataclass
+class FriOracleInfo:
+    num_polys: int
+    blinding: bool
+
+
+@dataclass
+class FriBatchInfo:
+    point: Tuple[int, int]
+    polynomials: List[FriPolynomialInfo]
+
+
+@dataclass
+class FriInstanceInfo:
+    oracles: List[FriOracleInfo]
+    batches: List[FriBatchInfo]
+
+
+# ---- proof (fri/proof.rs) -----------------------------------------------------------------------------------------
+@dataclass
+class FriQueryStep:
+    evals: np.ndarray            # [arity][2]
+    merkle_proof: MerkleProof
+
+
+@dataclass
+class FriInitialTreeProof:
+    evals_proofs: List[Tuple[np.ndarray, MerkleProof]]
+
+
+@dataclass
+class FriQueryRound:
+    initial_trees_proof: FriInitialTreeProof
+    steps: List[FriQueryStep]
+
+
+@dataclass
+class FriProof:
+    commit_phase_merkle_caps: List[MerkleCap]
+    query_round_proofs: List[FriQueryRound]
+    final_poly: np.ndarray       # PolynomialCoeffs<F::Extension>, [len][2]
+    pow_witness: int
+    fri_query_indices: List[int] = field(default_factory=list)   # not serialised by the reference; kept for tests
+
+
+# ---- device-resident extension polynomial ---------------------------------------------------------------------------
+class ExtensionPolynomial:
+    """PolynomialCoeffs<F::Extension> held on the device (pcs_ext_poly)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def from_coeffs(cls, coeffs):
+        c = _ffi.as_u64(coeffs).reshape(-1, 2)
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().pcs_ext_poly_new(_ffi.ptr(c), c.shape[0], C.byref(h)))
+        return cls(h)
+
+    def __len__(self):
+        n = C.c_size_t()
+        _ffi.check(_ffi.lib().pcs_ext_poly_len(self._h, C.byref(n)))
+        return int(n.value)
+
+    @property
+    def coeffs(self):
+        out = np.empty((len(self), 2), dtype=np.uint64)
+        _ffi.check(_ffi.lib().pcs_ext_poly_read(self._h, _ffi.ptr(out)))
+        return out
+
+    def lde_coset_fft(self, rate_bits, shift=COSET_SHIFT):
+        """self.lde(rate_bits).coset_fft(shift.into()): values in natural order, [len << rate_bits][2]."""
+        out = np.empty((len(self) << rate_bits, 2), dtype=np.uint64)
+        _ffi.check(_ffi.lib().pcs_ext_coset_lde(self._h, rate_bits, int(shift) % P, _ffi.ptr(out)))
+        return out
+
+    def commit_layer(self, rate_bits, shift, arity_bits, cap_height):
+        """One tree of fri_committed_trees (prover.rs:81-87) -> device-resident MerkleTree view."""
+        n_leaves = (len(self) << rate_bits) >> arity_bits
+        if cap_height > log2_strict(n_leaves):
+            raise ValueError(f"cap_height={cap_height} should be at most log2(leaves.len())={log2_strict(n_leaves)}")
+        cap = np.empty((1 << cap_height, 4), dtype=np.uint64)
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().pcs_fri_commit_layer(self._h, rate_bits, int(shift) % P, arity_bits, cap_height,
+                                                   _ffi.ptr(cap), C.byref(h)))
+        t = PolynomialBatch()
+        t._h, t._cap, t._coeffs_host = h, cap, []
+        t.degree_log, t.rate_bits, t.blinding, t.cap_height = log2_strict(n_leaves), 0, False, cap_height
+        t.n_polys, t.salt_w, t.n_leaves = 2 << arity_bits, 0, n_leaves
+        t.n_digests = 2 * (n_leaves - (1 << cap_height))
+        t.merkle_tree = _DeviceMerkleTree(t)
+        return t
+
+    def fold(self, arity_bits, beta):
+        """prover.rs:93-101, in place."""
+        _ffi.check(_ffi.lib().pcs_fri_fold(self._h, arity_bits, _ext_arg(beta)))
+
+    def free(self):
+        if self._h is not None:
+            _ffi.lib().pcs_ext_poly_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---- openings (plonk/proof.rs:316-322) ----------------------------------------------------------------------------
+def eval_commitment(z, batch):
+    """c.polynomials.par_iter().map(|p| p.to_extension().eval(z)) -> [w][2], on the device."""
+    out = np.empty((batch.n_polys, 2), dtype=np.uint64)
+    _ffi.check(_ffi.lib().pcs_batch_eval_ext(batch._h, _ext_arg(z), _ffi.ptr(out)))
+    return out
+
+
+# ---- prover (fri/oracle.rs:162-219, fri/prover.rs) ------------------------------------------------------------------
+def final_poly(instance, oracles, alpha):
+    """The polynomial FRI runs on (oracle.rs:171-200), before .lde(rate_bits)."""
+    total = sum(len(b.polynomials) for b in instance.batches)
+    points = np.array([[int(b.point[0]) % P, int(b.point[1]) % P] for b in instance.batches], dtype=np.uint64)
+    lens = (C.c_size_t * len(instance.batches))(*[len(b.polynomials) for b in instance.batches])
+    oi = np.fromiter((p.oracle_index for b in instance.batches for p in b.polynomials), dtype=np.uint32, count=total)
+    pi = np.fromiter((p.polynomial_index for b in instance.batches for p in b.polynomials), dtype=np.uint32, count=total)
+    handles = (C.c_void_p * len(oracles))(*[o._h for o in oracles])
+    h = C.c_void_p()
+    _ffi.check(_ffi.lib().pcs_fri_final_poly(handles, len(oracles), len(instance.batches), _ffi.ptr(points), lens,
+                                             oi.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                             pi.ctypes.data_as(C.POINTER(C.c_uint32)), _ext_arg(alpha), C.byref(h)))
+    return ExtensionPolynomial(h)
+
+
+def fri_committed_trees(poly, challenger, fri_params):
+    """prover.rs:69-112.  `poly`: the d non-zero coefficients of lde_polynomial_coeffs (the LDE padding is implicit);
+    consumed (folded in place).  Returns (trees, final_coeffs [len][2])."""
+    trees = []
+    shift = COSET_SHIFT
+    rate_bits, cap_height = fri_params.config.rate_bits, fri_params.config.cap_height
+    for arity_bits in fri_params.reduction_arity_bits:
+        tree = poly.commit_layer(rate_bits, shift, arity_bits, cap_height)
+        challenger.observe_cap(tree.merkle_tree.cap)
+        trees.append(tree)
+        beta = challenger.get_extension_challenge()
+        poly.fold(arity_bits, beta)
+        shift = pow(shift, 1 << arity_bits, P)
+    final_coeffs = poly.coeffs   # coeffs.truncate(len >> rate_bits): exactly the coefficients held
+    challenger.observe_extension_elements([(int(a), int(b)) for a, b in final_coeffs])
+    return trees, final_coeffs
+
+
+def fri_prover_query_round(initial_merkle_trees, trees, x_index, fri_params):
+    """prover.rs:183-216"""
+    initial = [(t.merkle_tree.get(x_index), t.merkle_tree.prove(x_index)) for t in initial_merkle_trees]
+    steps = []
+    for i, tree in enumerate(trees):
+        arity_bits = fri_params.reduction_arity_bits[i]
+        evals = tree.merkle_tree.get(x_index >> arity_bits).reshape(-1, 2)   # unflatten
+        steps.append(FriQueryStep(evals=evals, merkle_proof=tree.merkle_tree.prove(x_index >> arity_bits)))
+        x_index >>= arity_bits
+    return FriQueryRound(FriInitialTreeProof(initial), steps)
+
+
+def fri_proof(initial_merkle_trees, poly, challenger, fri_params):
+    """prover.rs:20-67.  `initial_merkle_trees`: the committed batches (their trees serve the query phase)."""
+    n = len(poly) << fri_params.config.rate_bits
+    trees, final_coeffs = fri_committed_trees(poly, challenger, fri_params)
+    # PoW phase (prover.rs:115-160): search on the device, then replay through the transcript
+    pow_witness = fri_proof_of_work(challenger.sponge_state.state, challenger.input_buffer, fri_params.config)
+    challenger.observe_element(pow_witness)
+    pow_response = challenger.get_challenge()
+    assert pow_response < (1 << (64 - fri_params.config.proof_of_work_bits)) or fri_params.config.proof_of_work_bits == 0
+    # query phase (prover.rs:162-181)
+    indices = [r % n for r in challenger.get_n_challenges(fri_params.config.num_query_rounds)]
+    rounds = [fri_prover_query_round(initial_merkle_trees, trees, x, fri_params) for x in indices]
+    proof = FriProof(commit_phase_merkle_caps=[t.merkle_tree.cap for t in trees], query_round_proofs=rounds,
+                     final_poly=final_coeffs, pow_witness=pow_witness, fri_query_indices=indices)
+    for t in trees:
+        t.free()
+    return proof
+
+
+def prove_openings(instance, oracles, challenger, fri_params, timing=None):
+    """PolynomialBatch::prove_openings (oracle.rs:162-219): a batch opening proof for `instance` over the committed
+    `oracles` (which must hold their coefficients on the device: from_values, or from_coeffs(keep_coeffs=True))."""
+    alpha = challenger.get_extension_challenge()
+    poly = final_poly(instance, oracles, alpha)
+    assert len(poly) == 1 << fri_params.degree_bits
+    try:
+        return fri_proof(oracles, poly, challenger, fri_params)
+    finally:
+        poly.free()
+
+
+PolynomialBatch.prove_openings = staticmethod(prove_openings)
