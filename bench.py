@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--cpu-sample-lg-d", type=int, default=16, help="degree_log of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fri", action="store_true", help="skip the opening-proof (FRI) timings")
     ap.add_argument("--chunks", type=int, default=2,
                     help="N > 1: polynomial groups of the streaming exchange (1 = one all-gather, then the LDE)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer"],
@@ -190,6 +191,88 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def fri_opening_bench(pcs, w, lg_d, r, cap_h, dev_ptrs, steps, peak_gbs):
+    """SURVEY 8f N2/N3 at the headline shape: the opening proof over ONE committed batch of w polynomials of degree
+    2^lg_d (coefficients kept on the device): every polynomial opened at zeta, the first 20 also at g*zeta (the shape of
+    the reference's instance, circuit_data.rs:461-481), standard_recursion_config FRI parameters.  Times are CUDA events
+    on the engine's stream around the public calls (each ends with its own small D2H copy)."""
+    import torch
+    from plonky2_demo_b200 import _ffi
+    from plonky2_demo_b200 import fri_prover as fp
+
+    L = _ffi.lib()
+    d = 1 << lg_d
+    h = C.c_void_p()
+    _ffi.check(L.pcs_commit_from_coeffs(dev_ptrs, w, lg_d, r, cap_h, None, 0, _ffi.PCS_DEVICE_PTRS | _ffi.PCS_KEEP_COEFFS,
+                                        None, C.byref(h)))
+    b = pcs.PolynomialBatch()
+    b._h, b._coeffs_host = h, []
+    b.degree_log, b.rate_bits, b.blinding, b.cap_height = lg_d, r, False, cap_h
+    b.n_polys, b.salt_w, b.n_leaves = w, 0, d << r
+    b.n_digests = 2 * ((d << r) - (1 << cap_h))
+    cap = np.empty((1 << cap_h, 4), dtype=np.uint64)
+    _ffi.check(L.pcs_batch_cap(h, _ffi.ptr(cap)))
+    b._cap = cap
+    from plonky2_demo_b200.fri import _DeviceMerkleTree
+    b.merkle_tree = _DeviceMerkleTree(b)
+
+    stream = torch.cuda.current_stream()
+
+    def timed(fn, reps):
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(reps):
+            out = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, out
+
+    zeta = (0x0123456789ABCDEF % fp.P, 0x0FEDCBA987654321 % fp.P)
+    g = fp.primitive_root_of_unity(lg_d)
+    zeta_next = fp.ext_mul((g, 0), zeta)
+    n_next = min(20, w)
+    inst = fp.FriInstanceInfo(
+        oracles=[fp.FriOracleInfo(w, False)],
+        batches=[fp.FriBatchInfo(zeta, fp.FriPolynomialInfo.from_range(0, range(w))),
+                 fp.FriBatchInfo(zeta_next, fp.FriPolynomialInfo.from_range(0, range(n_next)))])
+    alpha = (0x1111111122222222 % fp.P, 0x3333333344444444 % fp.P)
+
+    eval_ms, opened = timed(lambda: fp.eval_commitment(zeta, b), steps)
+
+    def fin():
+        p = fp.final_poly(inst, [b], alpha)
+        p.free()
+    fin_ms, _ = timed(fin, steps)
+
+    cfg = pcs.CircuitConfig.standard_recursion_config().fri_config
+    cfg = pcs.FriConfig(r, cap_h, cfg.proof_of_work_bits, cfg.reduction_strategy, cfg.num_query_rounds)
+    params = cfg.fri_params(lg_d, False)
+
+    def prove():
+        ch = fp.Challenger()
+        ch.observe_cap(b.merkle_tree.cap)
+        ch.observe_extension_elements([(int(x), int(y)) for x, y in opened[:8]])
+        return fp.prove_openings(inst, [b], ch, params)
+    prove_ms, proof = timed(prove, max(1, steps // 2))
+    eval_bytes = w * d * 8
+    fin_bytes = (w + n_next) * d * 8 + 2 * (2 * d * 16 * 3)   # coefficients once per batch + the extension-poly passes
+    out = {
+        "workload": f"opening proof over {w} polys x 2^{lg_d} (all at zeta, {n_next} at g*zeta), rate_bits {r}, "
+                    f"arities {params.reduction_arity_bits}, {cfg.num_query_rounds} queries, {cfg.proof_of_work_bits} PoW bits",
+        "eval_commitment": {"ms": eval_ms, "algorithmic_bytes": eval_bytes, "GBps": eval_bytes / (eval_ms * 1e-3) / 1e9,
+                            "frac_hbm": eval_bytes / (eval_ms * 1e-3) / 1e9 / peak_gbs},
+        "final_poly": {"ms": fin_ms, "algorithmic_bytes": fin_bytes, "GBps": fin_bytes / (fin_ms * 1e-3) / 1e9,
+                       "frac_hbm": fin_bytes / (fin_ms * 1e-3) / 1e9 / peak_gbs},
+        "prove_openings": {"ms": prove_ms, "final_poly_len": int(proof.final_poly.shape[0]),
+                           "commit_phase_trees": len(proof.commit_phase_merkle_caps),
+                           "note": "host transcript (Challenger) + device kernels; includes PoW grinding and 28 query rounds"},
+    }
+    b.free()
+    return out
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -333,6 +416,11 @@ def run_ours(a):
         lde_alone = g0.elapsed_time(g1) / a.steps
         del lde_out
 
+    # ---- the opening proof over the committed batch (single GPU) ----
+    fri = None
+    if world == 1 and not a.no_fri:
+        fri = fri_opening_bench(pcs, w, lg_d, r, cap_h, dev_ptrs, a.steps, float(measured_peaks()[0]["hbm_gbs"]))
+
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
     e2e = None
     if not a.no_e2e:
@@ -392,6 +480,7 @@ def run_ours(a):
         "lde": {"ms": lde_ms, "algorithmic_bytes": lde_bytes, "GBps": lde_bytes / (lde_ms * 1e-3) / 1e9, "frac_hbm": lde_bytes / (lde_ms * 1e-3) / 1e9 / peak},
         "leaf_hash": {"ms": leaf_ms, "algorithmic_bytes": leaf_bytes, "GBps": roofline["achieved"], "frac_hbm": roofline["frac"], "permutations": n_perm_leaf},
         "node_levels": {"ms": node_ms, "algorithmic_bytes": node_bytes, "GBps": node_bytes / (node_ms * 1e-3) / 1e9, "permutations": n_perm_node},
+        "fri_opening": fri,
         "commit": {"ms": ms_per_step, "algorithmic_bytes": commit_bytes, "GBps": commit_bytes / (ms_per_step * 1e-3) / 1e9,
                    "frac_hbm": commit_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
     }

@@ -162,6 +162,9 @@ PCS_API int pcs_batch_leaves(const pcs_batch* b, size_t first, size_t count, uin
 PCS_API int pcs_batch_get_rows(const pcs_batch* b, const uint64_t* leaf_indices, size_t n, uint64_t* rows /*[n][leaf_len]*/);
 /* MerkleTree::prove(leaf_index): siblings bottom-up, [log2 N - cap_height][4].  merkle_tree.rs:173-207 */
 PCS_API int pcs_batch_prove(const pcs_batch* b, size_t leaf_index, uint64_t* siblings);
+/* The same for n leaves in one call: siblings [n][log2 N - cap_height][4] (the FRI query phase asks every tree for
+ * num_query_rounds paths, fri/prover.rs:162-216).                                                    */
+PCS_API int pcs_batch_prove_many(const pcs_batch* b, const uint64_t* leaf_indices, size_t n, uint64_t* siblings);
 /* polynomials[i].coeffs (needs PCS_KEEP_COEFFS or from_values).                                     */
 PCS_API int pcs_batch_coeffs(const pcs_batch* b, size_t poly, uint64_t* coeffs /*[d]*/);
 /* All of `polynomials` at once as one [w][d] matrix.                                                  */

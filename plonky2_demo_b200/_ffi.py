@@ -44,6 +44,7 @@ SIGNATURES = {
     "pcs_batch_leaves": (C.c_int, [C.c_void_p, sz, sz, u64p]),
     "pcs_batch_get_rows": (C.c_int, [C.c_void_p, u64p, sz, u64p]),
     "pcs_batch_prove": (C.c_int, [C.c_void_p, sz, u64p]),
+    "pcs_batch_prove_many": (C.c_int, [C.c_void_p, u64p, sz, u64p]),
     "pcs_batch_coeffs": (C.c_int, [C.c_void_p, sz, u64p]),
     "pcs_batch_all_coeffs": (C.c_int, [C.c_void_p, u64p]),
     "pcs_batch_lde_dev": (C.c_void_p, [C.c_void_p]),

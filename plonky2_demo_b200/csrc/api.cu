@@ -794,6 +794,23 @@ int pcs_batch_prove(const pcs_batch* b, size_t leaf_index, uint64_t* siblings) {
     return PCS_OK;
 }
 
+int pcs_batch_prove_many(const pcs_batch* b, const uint64_t* leaf_indices, size_t n, uint64_t* siblings) {
+    if (!b || (n && !leaf_indices)) return fail(PCS_ERR_ARG, "NULL pointer");
+    for (size_t k = 0; k < n; k++)
+        if (leaf_indices[k] >= b->n) return fail(PCS_ERR_ARG, "leaf index out of bounds");
+    unsigned lg_sub = b->lg_d + b->rate_bits - b->cap_height;
+    if (lg_sub == 0 || n == 0) return PCS_OK;
+    if (!siblings) return fail(PCS_ERR_ARG, "NULL pointer");
+    cudaStream_t st = g_ctx.stream;
+    DevBuf o;
+    PCS_CUDA(o.alloc(n * lg_sub * 32, st));
+    for (size_t k = 0; k < n; k++)
+        PCS_CUDA(launch_prove(b->digests, lg_sub, leaf_indices[k], o.u64() + k * lg_sub * 4, st));
+    PCS_CUDA(cudaMemcpyAsync(siblings, o.p, n * lg_sub * 32, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
 int pcs_batch_coeffs(const pcs_batch* b, size_t poly, uint64_t* coeffs) {
     if (!b || !coeffs) return fail(PCS_ERR_ARG, "NULL pointer");
     if (!b->coeffs) return fail(PCS_ERR_ARG, "coefficients were not kept (PCS_KEEP_COEFFS)");

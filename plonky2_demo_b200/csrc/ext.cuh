@@ -47,6 +47,79 @@ __device__ __forceinline__ uint64_t acc_reduce(const acc160& A) {
     return sub_lc(reduce128(A.lo, A.hi), (uint64_t)A.top << 32);
 }
 
+// ---- carry-free lazy accumulation: sum_k c_k * w_k for canonical multipliers w_k held as 22-bit limbs -----------
+// w = w0 + w1 2^22 + w2 2^44 (w0, w1 < 2^22, w2 < 2^20) and c = c0 + c1 2^32: the six partial products c_i w_j are
+// below 2^54, so each of the six weights gets its own 64-bit accumulator and up to 1024 terms are added with one plain
+// IMAD.WIDE.U32 each -- no carry chains (a 64x64 product with 160-bit accumulation costs ~20 instructions, half of them
+// carry-chained; profiles/r01_fri_kernels.md).  The accumulators are recombined once per sum.
+struct limbs22 {
+    uint32_t w0, w1, w2;
+};
+
+__host__ __device__ __forceinline__ limbs22 split22(uint64_t w) {
+    limbs22 l;
+    l.w0 = (uint32_t)(w & 0x3FFFFF);
+    l.w1 = (uint32_t)((w >> 22) & 0x3FFFFF);
+    l.w2 = (uint32_t)(w >> 44);
+    return l;
+}
+
+struct lazy6 {
+    uint64_t a00, a01, a02, a10, a11, a12;   // weights 2^0, 2^22, 2^44, 2^32, 2^54, 2^76
+};
+constexpr int LAZY_MAX_TERMS = 1024;
+
+__device__ __forceinline__ void lazy_zero(lazy6& A) { A.a00 = A.a01 = A.a02 = A.a10 = A.a11 = A.a12 = 0; }
+
+// acc += a * b as ONE IMAD.WIDE.U32 (inline PTX: nvcc otherwise re-associates the sums into fresh products plus 64-bit adds)
+__device__ __forceinline__ void mad_wide(uint64_t& acc, uint32_t a, uint32_t b) {
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(b));
+}
+
+__device__ __forceinline__ void lazy_mac(lazy6& A, uint64_t c, uint32_t w0, uint32_t w1, uint32_t w2) {
+    const uint32_t c0 = (uint32_t)c, c1 = (uint32_t)(c >> 32);
+    mad_wide(A.a00, c0, w0);
+    mad_wide(A.a01, c0, w1);
+    mad_wide(A.a02, c0, w2);
+    mad_wide(A.a10, c1, w0);
+    mad_wide(A.a11, c1, w1);
+    mad_wide(A.a12, c1, w2);
+}
+
+// S += v << s  (0 < s < 64)
+__device__ __forceinline__ void acc_add_shl(acc160& S, uint64_t v, int s) {
+    uint64_t l = v << s, h = v >> (64 - s);
+    asm("{\n\t"
+        "add.cc.u64  %0, %0, %3;\n\t"
+        "addc.cc.u64 %1, %1, %4;\n\t"
+        "addc.u32    %2, %2, 0;\n\t"
+        "}"
+        : "+l"(S.lo), "+l"(S.hi), "+r"(S.top)
+        : "l"(l), "l"(h));
+}
+
+__device__ __forceinline__ uint64_t lazy_reduce(const lazy6& A) {
+    acc160 S;
+    S.lo = A.a00;
+    S.hi = 0;
+    S.top = 0;
+    acc_add_shl(S, A.a01, 22);
+    acc_add_shl(S, A.a10, 32);
+    acc_add_shl(S, A.a02, 44);
+    acc_add_shl(S, A.a11, 54);
+    {   // a12 << 76 = (a12 << 12) at weight 2^64
+        uint64_t h = A.a12 << 12;
+        uint32_t t = (uint32_t)(A.a12 >> 52);
+        asm("{\n\t"
+            "add.cc.u64  %0, %0, %2;\n\t"
+            "addc.u32    %1, %1, %3;\n\t"
+            "}"
+            : "+l"(S.hi), "+r"(S.top)
+            : "l"(h), "r"(t));
+    }
+    return acc_reduce(S);
+}
+
 // loose x loose -> loose.  c0 = a0 b0 + 7 a1 b1, c1 = a0 b1 + a1 b0, each as ONE lazy reduction
 __device__ __forceinline__ ext2 ext_mul(ext2 x, ext2 y) {
     acc160 c0, c1;

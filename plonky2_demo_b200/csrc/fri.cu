@@ -11,12 +11,13 @@
 // reference's Vec<F::Extension> exists only at the host boundary.
 //
 // The two kernels that touch a whole committed batch (k_eval_ext, k_reduce_polys_base) read every coefficient once
-// and are HBM bound: products are accumulated unreduced in 160 bits (ext.cuh) so that a coefficient costs two
-// 64x64 products and two carry chains, not two modular multiplications.
+// and should be HBM bound: the multipliers (powers of z / alpha) are held as 22-bit limbs so that a coefficient costs
+// twelve plain IMAD.WIDE.U32 into twelve 64-bit accumulators -- no carry chains, no modular reduction (ext.cuh lazy6).
 #include <vector>
 
 #include "common.cuh"
 #include "ext.cuh"
+#include "tma.cuh"
 
 using namespace pcs;
 
@@ -64,39 +65,143 @@ __global__ void k_interleave_bitrev(const uint64_t* in, size_t n, unsigned lg_n,
 // ------------------------------------------------------------------------------------------------
 // eval_commitment: P_j(z) for every polynomial of a batch, z in the extension
 // ------------------------------------------------------------------------------------------------
-constexpr int EV_THREADS = 256, EV_PER_THREAD = 16, EV_CHUNK = EV_THREADS * EV_PER_THREAD;
+constexpr int EV_THREADS = 256, EV_PER_THREAD = 64, EV_BATCH = 16, EV_CHUNK = EV_THREADS * EV_PER_THREAD;
 
-// grid (chunks, w).  Thread t of chunk c sums  coeff[c*4096 + t + 256 k] * (z^256)^k  over k < 16 unreduced, multiplies
-// by z^t, the block adds its 256 partial sums and scales by z^(4096 c).
+// grid (chunks, w).  Thread t of chunk c sums  coeff[c*16384 + t + 256 k] * (z^256)^k  over k < 64 carry-free (ext.cuh
+// lazy6, loads double-buffered in batches of 16), multiplies by z^t; the block adds its 256 partial sums and scales by z^(16384 c).
 __global__ void __launch_bounds__(EV_THREADS) k_eval_ext(const uint64_t* __restrict__ coeffs, size_t d,
                                                          const gl::ext2* __restrict__ pw_t /*[256] z^t*/,
-                                                         const gl::ext2* __restrict__ pw_k /*[16] z^(256 k)*/,
-                                                         const gl::ext2* __restrict__ pw_c /*[chunks] z^(4096 c)*/,
+                                                         const gl::ext2* __restrict__ pw_k /*[64] z^(256 k)*/,
+                                                         const gl::ext2* __restrict__ pw_c /*[chunks] z^(16384 c)*/,
                                                          gl::ext2* __restrict__ partial /*[w][chunks]*/) {
-    __shared__ gl::ext2 s_k[EV_PER_THREAD];
+    __shared__ uint32_t s_k[EV_PER_THREAD][8];   // 22-bit limbs of (z^256)^k: a part in [0..2], b part in [4..6]
     __shared__ gl::ext2 s_red[EV_THREADS / 32];
     const unsigned t = threadIdx.x;
-    if (t < EV_PER_THREAD) s_k[t] = pw_k[t];
+    if (t < EV_PER_THREAD) {
+        gl::ext2 w = pw_k[t];
+        gl::limbs22 la = gl::split22(w.a), lb = gl::split22(w.b);
+        s_k[t][0] = la.w0; s_k[t][1] = la.w1; s_k[t][2] = la.w2; s_k[t][3] = 0;
+        s_k[t][4] = lb.w0; s_k[t][5] = lb.w1; s_k[t][6] = lb.w2; s_k[t][7] = 0;
+    }
     __syncthreads();
     const uint64_t* poly = coeffs + (size_t)blockIdx.y * d;
     const size_t base = (size_t)blockIdx.x * EV_CHUNK + t;
-    uint64_t c[EV_PER_THREAD];
+    gl::lazy6 A, B;   // 64 terms each: far below LAZY_MAX_TERMS
+    gl::lazy_zero(A);
+    gl::lazy_zero(B);
+    // software pipeline: the loads of batch b + 1 are in flight while batch b is multiplied
+    uint64_t cur[EV_BATCH], nxt[EV_BATCH];
 #pragma unroll
-    for (int k = 0; k < EV_PER_THREAD; k++) {
+    for (int k = 0; k < EV_BATCH; k++) {
         size_t i = base + (size_t)k * EV_THREADS;
-        c[k] = i < d ? poly[i] : 0;
+        cur[k] = i < d ? poly[i] : 0;
     }
-    gl::acc160 A, B;
-    gl::acc_zero(A);
-    gl::acc_zero(B);
+#pragma unroll 1
+    for (int k0 = 0; k0 < EV_PER_THREAD; k0 += EV_BATCH) {
 #pragma unroll
-    for (int k = 0; k < EV_PER_THREAD; k++) {
-        gl::acc_mac(A, c[k], s_k[k].a);
-        gl::acc_mac(B, c[k], s_k[k].b);
+        for (int k = 0; k < EV_BATCH; k++) {
+            size_t i = base + (size_t)(k0 + EV_BATCH + k) * EV_THREADS;
+            nxt[k] = (k0 + EV_BATCH < EV_PER_THREAD && i < d) ? poly[i] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < EV_BATCH; k++) {
+            const uint4 wa = *reinterpret_cast<const uint4*>(&s_k[k0 + k][0]);
+            const uint4 wb = *reinterpret_cast<const uint4*>(&s_k[k0 + k][4]);
+            gl::lazy_mac(A, cur[k], wa.x, wa.y, wa.z);
+            gl::lazy_mac(B, cur[k], wb.x, wb.y, wb.z);
+        }
+#pragma unroll
+        for (int k = 0; k < EV_BATCH; k++) cur[k] = nxt[k];
     }
-    gl::ext2 s = {gl::acc_reduce(A), gl::acc_reduce(B)};
+    gl::ext2 s = {gl::lazy_reduce(A), gl::lazy_reduce(B)};
     s = gl::ext_canon(gl::ext_mul(s, pw_t[t]));
     // block sum (canonical adds)
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        uint64_t oa = __shfl_down_sync(0xffffffffu, s.a, off), ob = __shfl_down_sync(0xffffffffu, s.b, off);
+        s.a = gl::add(s.a, oa);
+        s.b = gl::add(s.b, ob);
+    }
+    if ((t & 31) == 0) s_red[t >> 5] = s;
+    __syncthreads();
+    if (t == 0) {
+        for (int wp = 1; wp < EV_THREADS / 32; wp++) {
+            s.a = gl::add(s.a, s_red[wp].a);
+            s.b = gl::add(s.b, s_red[wp].b);
+        }
+        partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = gl::ext_canon(gl::ext_mul(s, pw_c[blockIdx.x]));
+    }
+}
+
+// The same sum with the coefficients staged through shared memory by the TMA unit: a block owns 128 KB of ONE polynomial
+// (16384 coefficients); one elected thread streams it as bulk copies of 16 KB (8 k-steps) into a two-slot ring, each slot
+// completing on its own mbarrier, so 16-32 KB per block are in flight whatever the register budget.  Needs d % 256 == 0.
+constexpr int EV_GROUP = 8;                                   // k-steps (of 256 coefficients) per bulk copy
+__global__ void __launch_bounds__(EV_THREADS) k_eval_ext_tma(const uint64_t* __restrict__ coeffs, size_t d,
+                                                             const gl::ext2* __restrict__ pw_t, const gl::ext2* __restrict__ pw_k,
+                                                             const gl::ext2* __restrict__ pw_c, gl::ext2* __restrict__ partial) {
+    __shared__ __align__(128) uint64_t s_buf[2][EV_GROUP * EV_THREADS];   // 2 x 16 KB
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_k[EV_PER_THREAD][8];
+    __shared__ gl::ext2 s_red[EV_THREADS / 32];
+    const unsigned t = threadIdx.x;
+    if (t < EV_PER_THREAD) {
+        gl::ext2 w = pw_k[t];
+        gl::limbs22 la = gl::split22(w.a), lb = gl::split22(w.b);
+        s_k[t][0] = la.w0; s_k[t][1] = la.w1; s_k[t][2] = la.w2; s_k[t][3] = 0;
+        s_k[t][4] = lb.w0; s_k[t][5] = lb.w1; s_k[t][6] = lb.w2; s_k[t][7] = 0;
+    }
+    if (t == 0) {
+        tma::mbar_init(&s_bar[0], 1);
+        tma::mbar_init(&s_bar[1], 1);
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    const uint64_t* poly = coeffs + (size_t)blockIdx.y * d;
+    const size_t base = (size_t)blockIdx.x * EV_CHUNK;
+    const size_t left = d - base;                                            // > 0, multiple of 256
+    const int n_steps = (int)(left < (size_t)EV_CHUNK ? left / EV_THREADS : EV_PER_THREAD);
+    const int n_groups = (n_steps + EV_GROUP - 1) / EV_GROUP;
+    auto issue = [&](int g) {
+        const int steps = n_steps - g * EV_GROUP < EV_GROUP ? n_steps - g * EV_GROUP : EV_GROUP;
+        const uint32_t bytes = (uint32_t)steps * EV_THREADS * 8;
+        tma::mbar_arrive_expect_tx(&s_bar[g & 1], bytes);
+        tma::bulk_load(s_buf[g & 1], poly + base + (size_t)g * EV_GROUP * EV_THREADS, bytes, &s_bar[g & 1]);
+    };
+    if (t == 0) {
+        issue(0);
+        if (n_groups > 1) issue(1);
+    }
+    gl::lazy6 A, B;
+    gl::lazy_zero(A);
+    gl::lazy_zero(B);
+    for (int g = 0; g < n_groups; g++) {
+        const int steps = n_steps - g * EV_GROUP < EV_GROUP ? n_steps - g * EV_GROUP : EV_GROUP;
+        tma::mbar_wait(&s_bar[g & 1], (g >> 1) & 1);
+        const uint64_t* buf = s_buf[g & 1];
+        if (steps == EV_GROUP) {
+#pragma unroll
+            for (int k = 0; k < EV_GROUP; k++) {
+                const uint64_t c = buf[k * EV_THREADS + t];
+                const uint4 wa = *reinterpret_cast<const uint4*>(&s_k[g * EV_GROUP + k][0]);
+                const uint4 wb = *reinterpret_cast<const uint4*>(&s_k[g * EV_GROUP + k][4]);
+                gl::lazy_mac(A, c, wa.x, wa.y, wa.z);
+                gl::lazy_mac(B, c, wb.x, wb.y, wb.z);
+            }
+        } else {
+            for (int k = 0; k < steps; k++) {
+                const uint64_t c = buf[k * EV_THREADS + t];
+                const uint4 wa = *reinterpret_cast<const uint4*>(&s_k[g * EV_GROUP + k][0]);
+                const uint4 wb = *reinterpret_cast<const uint4*>(&s_k[g * EV_GROUP + k][4]);
+                gl::lazy_mac(A, c, wa.x, wa.y, wa.z);
+                gl::lazy_mac(B, c, wb.x, wb.y, wb.z);
+            }
+        }
+        __syncthreads();                                   // slot g & 1 has been read by everyone
+        if (t == 0 && g + 2 < n_groups) issue(g + 2);
+    }
+    gl::ext2 s = {gl::lazy_reduce(A), gl::lazy_reduce(B)};
+    s = gl::ext_canon(gl::ext_mul(s, pw_t[t]));
 #pragma unroll
     for (int off = 16; off; off >>= 1) {
         uint64_t oa = __shfl_down_sync(0xffffffffu, s.a, off), ob = __shfl_down_sync(0xffffffffu, s.b, off);
@@ -146,51 +251,146 @@ __global__ void __launch_bounds__(256) k_eval_sum(const gl::ext2* __restrict__ p
 // reduce_polys_base: F[i] = sum_j alpha^j f_j[i]   (util/reducing.rs:84-96)
 // ------------------------------------------------------------------------------------------------
 // One thread per coefficient index (coalesced over i for every polynomial), polynomials walked through a device pointer
-// table, alpha powers broadcast from shared memory, products accumulated unreduced.
-constexpr int RP_THREADS = 256, RP_TILE = 64;   // polynomials per shared-memory tile of (pointer, alpha^j)
+// table, alpha powers broadcast from shared memory as 22-bit limbs, products accumulated carry-free (ext.cuh lazy6).
+constexpr int RP_THREADS = 256, RP_TILE = 128, RP_GROUP = 8;   // polynomials per shared-memory tile of (pointer, alpha^j limbs)
+constexpr int RP_FLUSH = 512;                   // polynomials per carry-free accumulation run (<= LAZY_MAX_TERMS)
 
 __global__ void __launch_bounds__(RP_THREADS) k_reduce_polys_base(const uint64_t* const* __restrict__ polys, size_t n_polys,
                                                                   const gl::ext2* __restrict__ apow, size_t d,
                                                                   uint64_t* __restrict__ out /*[2][out_stride]*/,
                                                                   size_t out_stride) {
     __shared__ const uint64_t* s_ptr[RP_TILE];
-    __shared__ gl::ext2 s_pw[RP_TILE];
+    __shared__ uint32_t s_pw[RP_TILE][8];   // 22-bit limbs of alpha^j: a part in [0..2], b part in [4..6]
     const size_t i = (size_t)blockIdx.x * RP_THREADS + threadIdx.x;
-    gl::acc160 A, B;
-    gl::acc_zero(A);
-    gl::acc_zero(B);
+    const bool live = i < d;
+    uint64_t ra = 0, rb = 0;                // canonical running totals over the flushed runs
+    gl::lazy6 A, B;
+    gl::lazy_zero(A);
+    gl::lazy_zero(B);
+    size_t in_run = 0;
     for (size_t j0 = 0; j0 < n_polys; j0 += RP_TILE) {
         const int m = (int)(n_polys - j0 < RP_TILE ? n_polys - j0 : RP_TILE);
         __syncthreads();
         if ((int)threadIdx.x < m) {
             s_ptr[threadIdx.x] = polys[j0 + threadIdx.x];
-            s_pw[threadIdx.x] = apow[j0 + threadIdx.x];
+            gl::ext2 w = apow[j0 + threadIdx.x];
+            gl::limbs22 la = gl::split22(w.a), lb = gl::split22(w.b);
+            uint32_t* q = s_pw[threadIdx.x];
+            q[0] = la.w0; q[1] = la.w1; q[2] = la.w2; q[3] = 0;
+            q[4] = lb.w0; q[5] = lb.w1; q[6] = lb.w2; q[7] = 0;
         }
         __syncthreads();
-        if (i < d) {
-            int j = 0;
-            for (; j + 4 <= m; j += 4) {   // four loads in flight
-                uint64_t c0 = s_ptr[j][i], c1 = s_ptr[j + 1][i], c2 = s_ptr[j + 2][i], c3 = s_ptr[j + 3][i];
-                gl::acc_mac(A, c0, s_pw[j].a);
-                gl::acc_mac(B, c0, s_pw[j].b);
-                gl::acc_mac(A, c1, s_pw[j + 1].a);
-                gl::acc_mac(B, c1, s_pw[j + 1].b);
-                gl::acc_mac(A, c2, s_pw[j + 2].a);
-                gl::acc_mac(B, c2, s_pw[j + 2].b);
-                gl::acc_mac(A, c3, s_pw[j + 3].a);
-                gl::acc_mac(B, c3, s_pw[j + 3].b);
-            }
-            for (; j < m; j++) {
-                uint64_t c0 = s_ptr[j][i];
-                gl::acc_mac(A, c0, s_pw[j].a);
-                gl::acc_mac(B, c0, s_pw[j].b);
+        if (live) {
+            for (int j = 0; j < m; j += RP_GROUP) {   // eight loads in flight per thread
+                uint64_t c[RP_GROUP];
+#pragma unroll
+                for (int u = 0; u < RP_GROUP; u++) c[u] = j + u < m ? s_ptr[j + u][i] : 0;
+#pragma unroll
+                for (int u = 0; u < RP_GROUP; u++) {
+                    // rows past m hold stale limbs of an earlier tile, but their coefficient is 0
+                    const uint4 wa = *reinterpret_cast<const uint4*>(&s_pw[j + u][0]);
+                    const uint4 wb = *reinterpret_cast<const uint4*>(&s_pw[j + u][4]);
+                    gl::lazy_mac(A, c[u], wa.x, wa.y, wa.z);
+                    gl::lazy_mac(B, c[u], wb.x, wb.y, wb.z);
+                }
             }
         }
+        in_run += m;
+        if (in_run + RP_TILE > RP_FLUSH) {   // uniform across the block
+            ra = gl::add(ra, gl::canon(gl::lazy_reduce(A)));
+            rb = gl::add(rb, gl::canon(gl::lazy_reduce(B)));
+            gl::lazy_zero(A);
+            gl::lazy_zero(B);
+            in_run = 0;
+        }
     }
-    if (i < d) {
-        out[i] = gl::canon(gl::acc_reduce(A));
-        out[out_stride + i] = gl::canon(gl::acc_reduce(B));
+    if (live) {
+        out[i] = gl::add(ra, gl::canon(gl::lazy_reduce(A)));
+        out[out_stride + i] = gl::add(rb, gl::canon(gl::lazy_reduce(B)));
     }
+}
+
+// The same reduction with the coefficients staged through shared memory by the TMA unit: a block owns 256 columns; one
+// elected thread walks the polynomial pointer table and streams each polynomial's 2 KB slice as a bulk copy into a ring
+// of two half-rings of 8 slices, each half completing on its own mbarrier; the block multiplies half h while the copies
+// of the other half (and, after the release barrier, of the half after that) are in flight.  Needs d % 256 == 0.
+constexpr int RT_COLS = 256, RT_HALF = 8, RT_SUPER = 256;    // RT_SUPER polynomials per carry-free run (limbs in smem)
+__global__ void __launch_bounds__(RT_COLS) k_reduce_polys_base_tma(const uint64_t* const* __restrict__ polys, size_t n_polys,
+                                                                   const gl::ext2* __restrict__ apow, size_t d,
+                                                                   uint64_t* __restrict__ out, size_t out_stride) {
+    __shared__ __align__(128) uint64_t s_buf[2][RT_HALF][RT_COLS];   // 2 x 16 KB
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_pw[RT_SUPER][8];                            // 8 KB of alpha^j limbs
+    const unsigned t = threadIdx.x;
+    const size_t col0 = (size_t)blockIdx.x * RT_COLS;
+    if (t == 0) {
+        tma::mbar_init(&s_bar[0], 1);
+        tma::mbar_init(&s_bar[1], 1);
+        tma::fence_barrier_init();
+    }
+    uint64_t ra = 0, rb = 0;
+    uint32_t uses = 0;                                                // completed uses of the half ring pair, for the phase parity
+    for (size_t j0 = 0; j0 < n_polys; j0 += RT_SUPER) {
+        const int m = (int)(n_polys - j0 < (size_t)RT_SUPER ? n_polys - j0 : RT_SUPER);
+        __syncthreads();                                              // previous run's limbs / barriers are no longer in use
+        for (int j = t; j < m; j += RT_COLS) {
+            gl::ext2 w = apow[j0 + j];
+            gl::limbs22 la = gl::split22(w.a), lb = gl::split22(w.b);
+            uint32_t* q = s_pw[j];
+            q[0] = la.w0; q[1] = la.w1; q[2] = la.w2; q[3] = 0;
+            q[4] = lb.w0; q[5] = lb.w1; q[6] = lb.w2; q[7] = 0;
+        }
+        __syncthreads();
+        const int n_groups = (m + RT_HALF - 1) / RT_HALF;
+        auto issue = [&](int g) {
+            const int cnt = m - g * RT_HALF < RT_HALF ? m - g * RT_HALF : RT_HALF;
+            tma::mbar_arrive_expect_tx(&s_bar[g & 1], (uint32_t)cnt * RT_COLS * 8);
+            for (int u = 0; u < cnt; u++)
+                tma::bulk_load(s_buf[g & 1][u], polys[j0 + (size_t)g * RT_HALF + u] + col0, RT_COLS * 8, &s_bar[g & 1]);
+        };
+        if (t == 0) {
+            issue(0);
+            if (n_groups > 1) issue(1);
+        }
+        gl::lazy6 A, B;
+        gl::lazy_zero(A);
+        gl::lazy_zero(B);
+        for (int g = 0; g < n_groups; g++) {
+            const int cnt = m - g * RT_HALF < RT_HALF ? m - g * RT_HALF : RT_HALF;
+            tma::mbar_wait(&s_bar[g & 1], ((uses + g) >> 1) & 1);
+            if (cnt == RT_HALF) {
+#pragma unroll
+                for (int u = 0; u < RT_HALF; u++) {
+                    const uint64_t c = s_buf[g & 1][u][t];
+                    const uint4 wa = *reinterpret_cast<const uint4*>(&s_pw[g * RT_HALF + u][0]);
+                    const uint4 wb = *reinterpret_cast<const uint4*>(&s_pw[g * RT_HALF + u][4]);
+                    gl::lazy_mac(A, c, wa.x, wa.y, wa.z);
+                    gl::lazy_mac(B, c, wb.x, wb.y, wb.z);
+                }
+            } else {
+                for (int u = 0; u < cnt; u++) {
+                    const uint64_t c = s_buf[g & 1][u][t];
+                    const uint4 wa = *reinterpret_cast<const uint4*>(&s_pw[g * RT_HALF + u][0]);
+                    const uint4 wb = *reinterpret_cast<const uint4*>(&s_pw[g * RT_HALF + u][4]);
+                    gl::lazy_mac(A, c, wa.x, wa.y, wa.z);
+                    gl::lazy_mac(B, c, wb.x, wb.y, wb.z);
+                }
+            }
+            __syncthreads();                                          // half g & 1 has been read by everyone
+            if (t == 0 && g + 2 < n_groups) issue(g + 2);
+        }
+        // keep the two barriers' phases in step for the next run: both halves must have been used equally often
+        if (n_groups & 1) {
+            if (t == 0) tma::mbar_arrive_expect_tx(&s_bar[1], 0);     // an empty use of half 1
+            uses += n_groups + 1;
+        } else {
+            uses += n_groups;
+        }
+        ra = gl::add(ra, gl::canon(gl::lazy_reduce(A)));
+        rb = gl::add(rb, gl::canon(gl::lazy_reduce(B)));
+    }
+    out[col0 + t] = ra;
+    out[out_stride + col0 + t] = rb;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -328,8 +528,12 @@ int pcs_batch_eval_ext(const pcs_batch* b, const uint64_t point[2], uint64_t* ou
     if ((rc = pow_table(z, EV_THREADS, pw_t, st))) return rc;
     if ((rc = pow_table(glh::ext_pow(z, EV_THREADS), EV_PER_THREAD, pw_k, st))) return rc;
     if ((rc = pow_table(glh::ext_pow(z, EV_CHUNK), chunks, pw_c, st))) return rc;
-    k_eval_ext<<<dim3((unsigned)chunks, (unsigned)w), EV_THREADS, 0, st>>>(b->coeffs, d, pw_t, pw_k, pw_c,
-                                                                           (gl::ext2*)partial.p);
+    if (d % EV_THREADS == 0)   // TMA-staged (rows of a [w][d] matrix with d >= 256 are 16-byte aligned)
+        k_eval_ext_tma<<<dim3((unsigned)chunks, (unsigned)w), EV_THREADS, 0, st>>>(b->coeffs, d, pw_t, pw_k, pw_c,
+                                                                                   (gl::ext2*)partial.p);
+    else
+        k_eval_ext<<<dim3((unsigned)chunks, (unsigned)w), EV_THREADS, 0, st>>>(b->coeffs, d, pw_t, pw_k, pw_c,
+                                                                               (gl::ext2*)partial.p);
     PCS_CUDA(cudaGetLastError());
     k_eval_sum<<<(unsigned)w, 256, 0, st>>>((const gl::ext2*)partial.p, chunks, res.u64());
     PCS_CUDA(cudaGetLastError());
@@ -451,8 +655,12 @@ int pcs_fri_final_poly(const pcs_batch* const* oracles, size_t n_oracles, size_t
     size_t first = 0;
     for (size_t i = 0; i < n_batches; i++) {
         const size_t m = batch_len[i];
-        k_reduce_polys_base<<<blocks_for(d, RP_THREADS), RP_THREADS, 0, st>>>(
-            (const uint64_t* const*)table.p + first, m, (const gl::ext2*)apow.p, d, comp.u64(), d);
+        if (d % RT_COLS == 0)   // TMA-staged
+            k_reduce_polys_base_tma<<<(unsigned)(d / RT_COLS), RT_COLS, 0, st>>>(
+                (const uint64_t* const*)table.p + first, m, (const gl::ext2*)apow.p, d, comp.u64(), d);
+        else
+            k_reduce_polys_base<<<blocks_for(d, RP_THREADS), RP_THREADS, 0, st>>>(
+                (const uint64_t* const*)table.p + first, m, (const gl::ext2*)apow.p, d, comp.u64(), d);
         PCS_CUDA(cudaGetLastError());
         const glh::ext2 z = {points[2 * i] % glh::P, points[2 * i + 1] % glh::P};
         if ((rc = ext_suffix_scan(comp.u64(), d, d, z, comp.u64(), d, st))) return rc;     // quotient, last coefficient 0

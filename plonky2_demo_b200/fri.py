@@ -269,6 +269,14 @@ class PolynomialBatch:
             self._coeffs_host = out
         return [PolynomialCoeffs(c) for c in self._coeffs_host]
 
+    def prove_many(self, leaf_indices):
+        """MerkleTree::prove for several leaves in one device round trip -> list of MerkleProof."""
+        idx = np.ascontiguousarray(np.fromiter(leaf_indices, dtype=np.uint64))
+        k = log2_strict(self.n_leaves) - self.cap_height
+        sib = np.empty((idx.shape[0], k, 4), dtype=np.uint64)
+        _ffi.check(_ffi.lib().pcs_batch_prove_many(self._h, _ffi.ptr(idx), idx.shape[0], _ffi.ptr(sib)))
+        return [MerkleProof(s) for s in sib]
+
     def get_rows(self, indices):
         idx = np.ascontiguousarray(np.fromiter(indices, dtype=np.uint64))
         out = np.empty((idx.shape[0], self.n_polys + self.salt_w), dtype=np.uint64)

@@ -265,16 +265,26 @@ def fri_committed_trees(poly, challenger, fri_params):
     return trees, final_coeffs
 
 
-def fri_prover_query_round(initial_merkle_trees, trees, x_index, fri_params):
-    """prover.rs:183-216"""
-    initial = [(t.merkle_tree.get(x_index), t.merkle_tree.prove(x_index)) for t in initial_merkle_trees]
-    steps = []
+def fri_prover_query_rounds(initial_merkle_trees, trees, indices, fri_params):
+    """prover.rs:162-216 for all query indices at once: every tree serves its rows and paths in one device round trip
+    each (pcs_batch_get_rows / pcs_batch_prove_many) instead of one per query."""
+    n_q = len(indices)
+    init_rows = [t.get_rows(indices) for t in initial_merkle_trees]
+    init_paths = [t.prove_many(indices) for t in initial_merkle_trees]
+    step_rows, step_paths = [], []
+    cur = list(indices)
     for i, tree in enumerate(trees):
         arity_bits = fri_params.reduction_arity_bits[i]
-        evals = tree.merkle_tree.get(x_index >> arity_bits).reshape(-1, 2)   # unflatten
-        steps.append(FriQueryStep(evals=evals, merkle_proof=tree.merkle_tree.prove(x_index >> arity_bits)))
-        x_index >>= arity_bits
-    return FriQueryRound(FriInitialTreeProof(initial), steps)
+        cur = [x >> arity_bits for x in cur]
+        step_rows.append(tree.get_rows(cur))
+        step_paths.append(tree.prove_many(cur))
+    rounds = []
+    for q in range(n_q):
+        initial = [(init_rows[k][q], init_paths[k][q]) for k in range(len(initial_merkle_trees))]
+        steps = [FriQueryStep(evals=step_rows[i][q].reshape(-1, 2), merkle_proof=step_paths[i][q])   # unflatten
+                 for i in range(len(trees))]
+        rounds.append(FriQueryRound(FriInitialTreeProof(initial), steps))
+    return rounds
 
 
 def fri_proof(initial_merkle_trees, poly, challenger, fri_params):
@@ -288,7 +298,7 @@ def fri_proof(initial_merkle_trees, poly, challenger, fri_params):
     assert pow_response < (1 << (64 - fri_params.config.proof_of_work_bits)) or fri_params.config.proof_of_work_bits == 0
     # query phase (prover.rs:162-181)
     indices = [r % n for r in challenger.get_n_challenges(fri_params.config.num_query_rounds)]
-    rounds = [fri_prover_query_round(initial_merkle_trees, trees, x, fri_params) for x in indices]
+    rounds = fri_prover_query_rounds(initial_merkle_trees, trees, indices, fri_params)
     proof = FriProof(commit_phase_merkle_caps=[t.merkle_tree.cap for t in trees], query_round_proofs=rounds,
                      final_poly=final_coeffs, pow_witness=pow_witness, fri_query_indices=indices)
     for t in trees:
