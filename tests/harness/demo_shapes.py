@@ -40,6 +40,67 @@ def med(f, reps=5):
     return statistics.median(ts)
 
 
+def opening_proof(m, lg_d):
+    """OpeningSet::new + PolynomialBatch::prove_openings (plonk/proof.rs:316-344, fri/oracle.rs:162-219) over the four
+    committed oracles of one prove(): everything opened at zeta, the 2 Z polynomials also at g*zeta
+    (circuit_data.rs:461-481), standard_recursion_config.  GPU (engine + host transcript) against the CPU oracle
+    (C arithmetic + Python glue), proofs compared field by field."""
+    from oracle import fri_ref as fr
+    from plonky2_demo_b200 import fri_prover as fp
+
+    cfg = pcs.CircuitConfig.standard_recursion_config().fri_config
+    params = cfg.fri_params(lg_d, False)
+    coeffs = [seeded_polys(w, 1 << lg_d, base_seed=7000 * m + w) for _, w, _ in COMMITS]
+    gpu = [pcs.PolynomialBatch.from_coeffs(c, cfg.rate_bits, False, cfg.cap_height, keep_coeffs=True) for c in coeffs]
+    cpu = []
+    for c in coeffs:
+        o = oracle.commit_from_coeffs(c, cfg.rate_bits, cfg.cap_height)
+        o["coeffs"], o["cap_height"] = c, cfg.cap_height
+        cpu.append(o)
+    zeta = (0x0123456789ABCDEF % fp.P, 0x0FEDCBA987654321 % fp.P)
+    zeta_next = fp.ext_mul((fp.primitive_root_of_unity(lg_d), 0), zeta)
+    all_polys = [(k, j) for k, (_, w, _) in enumerate(COMMITS) for j in range(w)]
+    batches = [(zeta, all_polys), (zeta_next, [(2, 0), (2, 1)])]
+    inst = fp.FriInstanceInfo(
+        oracles=[fp.FriOracleInfo(w, False) for _, w, _ in COMMITS],
+        batches=[fp.FriBatchInfo(pt, [fp.FriPolynomialInfo(o, j) for o, j in polys]) for pt, polys in batches])
+
+    def gpu_openings():
+        at_zeta = [fp.eval_commitment(zeta, b) for b in gpu]
+        at_next = fp.eval_commitment(zeta_next, gpu[2])
+        return [[tuple(int(x) for x in at_zeta[o][j]) for o, j in all_polys], [tuple(int(x) for x in at_next[j]) for j in (0, 1)]]
+
+    openings = gpu_openings()
+
+    def transcript(cls):
+        ch = cls()
+        for o in cpu:
+            ch.observe_cap(o["cap"])
+        for vals in openings:
+            ch.observe_extension_elements(vals)
+        return ch
+
+    t0 = time.perf_counter()
+    want = fr.prove_openings(cpu, batches, transcript(fr.Challenger), cfg.rate_bits, cfg.cap_height, params.reduction_arity_bits,
+                             cfg.proof_of_work_bits, cfg.num_query_rounds)
+    cpu_ms = 1e3 * (time.perf_counter() - t0)
+    got = fp.prove_openings(inst, gpu, transcript(fp.Challenger), params)
+    same = (all(np.array_equal(c.hashes, wc) for c, wc in zip(got.commit_phase_merkle_caps, want["commit_phase_merkle_caps"]))
+            and np.array_equal(got.final_poly, want["final_poly"]) and got.pow_witness == want["pow_witness"]
+            and got.fri_query_indices == want["_indices"]
+            and all(np.array_equal(s.evals, ws["evals"]) for r, wr in zip(got.query_round_proofs, want["query_round_proofs"])
+                    for s, ws in zip(r.steps, wr["steps"])))
+    rec = {"polys_at_zeta": len(all_polys), "polys_at_zeta_next": 2, "arities": params.reduction_arity_bits,
+           "proof_equal_to_cpu_oracle": bool(same),
+           "gpu_openings_ms": med(gpu_openings, 3),
+           "gpu_prove_openings_ms": med(lambda: fp.prove_openings(inst, gpu, transcript(fp.Challenger), params), 3),
+           "cpu_oracle_prove_openings_ms": cpu_ms,
+           "note": "CPU figure = oracle/fri.c arithmetic (OpenMP where the reference uses rayon) + Python protocol glue, one run"}
+    for b in gpu:
+        b.free()
+    return rec
+
+
 def main():
     pcs.init(0)
     out = {"rate_bits": 3, "cap_height": 4, "cpu_threads": oracle.num_threads(), "configs": []}
@@ -67,6 +128,7 @@ def main():
             rec["fri_layer_trees"].append({"log_leaves": log_n, "leaf_len": 32, "cap_equal": bool(ok),
                                            "gpu_ms": med(lambda: pcs.MerkleTree.new(leaves, 4)),
                                            "cpu_port_ms": med(lambda: oracle.merkle_build(leaves, 4), 3)})
+        rec["opening_proof"] = opening_proof(m, lg_d)
         rec["gpu_ms_total"] = sum(c["gpu_ms"] for c in rec["commits"]) + sum(c["gpu_ms"] for c in rec["fri_layer_trees"])
         rec["cpu_port_ms_total"] = sum(c["cpu_port_ms"] for c in rec["commits"]) + sum(c["cpu_port_ms"] for c in rec["fri_layer_trees"])
         out["configs"].append(rec)
