@@ -12,6 +12,7 @@ Names, argument meaning and error behaviour follow the reference:
     PolynomialBatch                       plonky2/src/fri/oracle.rs:30-159 (+ prove_openings :162-219)
     Challenger                            plonky2/src/iop/challenger.rs:16-160
     FriInstanceInfo / FriProof            plonky2/src/fri/structure.rs, fri/proof.rs
+    Buffer (write_/read_polynomial_batch, _merkle_tree, _fri_proof)   plonky2/src/util/serialization/mod.rs
     PoseidonGoldilocksConfig              plonky2/src/plonk/config.rs:101-108
 
 All arithmetic runs in hand-written CUDA kernels (libpcs.so).  There is no CPU fallback: importing
@@ -52,6 +53,7 @@ from .polynomial import (  # noqa: F401
     reverse_index_bits,
 )
 from .runtime import init, shutdown, stream, synchronize  # noqa: F401
+from .serialization import Buffer, fri_proof_to_bytes, polynomial_batch_to_bytes  # noqa: F401
 
 __all__ = [
     "PolynomialBatch", "PolynomialValues", "PolynomialCoeffs", "MerkleTree", "MerkleCap", "MerkleProof",

@@ -332,3 +332,37 @@ def test_prove_openings_m64_demo_shape(pcs):
                                cfg.num_query_rounds, lg_d)
     for b in gpu:
         b.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# on-wire formats of device-resident data (util/serialization/mod.rs)
+# ---------------------------------------------------------------------------------------------
+def test_serialize_device_batch_and_proof(pcs):
+    from plonky2_demo_b200.fri_prover import Challenger, prove_openings
+    from plonky2_demo_b200.serialization import Buffer, fri_proof_to_bytes, polynomial_batch_to_bytes
+
+    lg_d, rate_bits, cap_height, widths = 6, 2, 2, [3, 4]
+    gpu, cpu, inst, batches = build_instance(pcs, lg_d, rate_bits, cap_height, widths, seed=5, from_values=True)
+    for b, o in zip(gpu, cpu):
+        data = polynomial_batch_to_bytes(b)
+        r = Buffer(data).read_polynomial_batch()
+        assert np.array_equal(np.stack([p.coeffs for p in r.polynomials]), o["coeffs"])
+        assert np.array_equal(r.merkle_tree.leaves, o["leaves"])
+        assert np.array_equal(r.merkle_tree.digests, o["digests"])
+        assert np.array_equal(r.merkle_tree.cap.hashes, o["cap"])
+        assert (r.degree_log, r.rate_bits, r.blinding) == (lg_d, rate_bits, False)
+        # polynomials (len + coeffs each), tree (leaves with lengths, digests with length, cap height, cap), 2 usize, 1 bool
+        w, d, n = o["coeffs"].shape[0], 1 << lg_d, (1 << lg_d) << rate_bits
+        assert len(data) == 8 + w * (d + 1) * 8 + 8 + n * (w + 1) * 8 + 8 + o["digests"].shape[0] * 32 + 8 + (32 << cap_height) + 17
+    cfg = pcs.FriConfig(rate_bits, cap_height, 4, pcs.FriReductionStrategy.Fixed([2, 1]), 3)
+    params = cfg.fri_params(lg_d, False)
+    ch = Challenger()
+    for o in cpu:
+        ch.observe_cap(o["cap"])
+    proof = prove_openings(inst, gpu, ch, params)
+    data = fri_proof_to_bytes(proof)
+    back = Buffer(data).read_fri_proof(widths, params.reduction_arity_bits, cap_height, 3, params.final_poly_len())
+    assert fri_proof_to_bytes(back) == data
+    assert back.pow_witness == proof.pow_witness and np.array_equal(back.final_poly, proof.final_poly)
+    for b in gpu:
+        b.free()
