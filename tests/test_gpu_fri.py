@@ -194,7 +194,10 @@ def build_instance(pcs, lg_d, rate_bits, cap_height, widths, seed=0, from_values
 
 
 @pytest.mark.parametrize("lg_d,widths", [(0, [1]), (1, [2, 1]), (6, [3, 5, 4, 2]), (9, [70, 3]), (13, [5, 2, 3]),
-                                         (15, [84, 135, 20, 16])])
+                                         (15, [84, 135, 20, 16]),
+                                         # more than 256 polynomials in one FRI batch: several carry-free runs per block,
+                                         # odd and even numbers of 8-polynomial groups (mbarrier phase bookkeeping)
+                                         (8, [257]), (9, [300, 3]), (8, [520, 9, 1]), (10, [248, 8]), (5, [1100])])
 def test_fri_final_poly(pcs, lg_d, widths):
     from plonky2_demo_b200.fri_prover import final_poly
 
