@@ -170,8 +170,11 @@ int pcs_pow_grind(const uint64_t* state, unsigned witness_pos, unsigned min_lead
     PCS_CUDA(cudaMemcpyAsync(d_state.p, state, 12 * 8, cudaMemcpyHostToDevice, st));
     const uint64_t P = 0xFFFFFFFF00000001ULL, none = ~0ULL;
     PCS_CUDA(cudaMemcpyAsync(d_best.p, &none, 8, cudaMemcpyHostToDevice, st));
-    // batches sized to the expected number of tries (2^min_lz), at least 2^20 and at most 2^26 candidates
-    uint64_t batch = (uint64_t)1 << (min_leading_zeros < 20 ? 20 : (min_leading_zeros > 26 ? 26 : min_leading_zeros));
+    // batches of four times the expected number of tries (2^min_lz): one launch finds the witness with probability
+    // 1 - e^-4; at least 2^14 and at most 2^26 candidates per launch.  Batches are searched in order and a batch returns its
+    // smallest hit, so the result is the smallest witness whatever the batch size.
+    const unsigned lg_batch = min_leading_zeros + 2 < 14 ? 14 : (min_leading_zeros + 2 > 26 ? 26 : min_leading_zeros + 2);
+    uint64_t batch = (uint64_t)1 << lg_batch;
     for (uint64_t base = 0; base < P; base += batch) {          // candidates 0 ..= p - 1 (prover.rs:141)
         uint64_t n = P - base < batch ? P - base : batch;
         PCS_CUDA(launch_pow_search(d_state.u64(), witness_pos, min_leading_zeros, base, n, (unsigned long long*)d_best.p, st));
@@ -802,10 +805,11 @@ int pcs_batch_prove_many(const pcs_batch* b, const uint64_t* leaf_indices, size_
     if (lg_sub == 0 || n == 0) return PCS_OK;
     if (!siblings) return fail(PCS_ERR_ARG, "NULL pointer");
     cudaStream_t st = g_ctx.stream;
-    DevBuf o;
+    DevBuf o, idx;
     PCS_CUDA(o.alloc(n * lg_sub * 32, st));
-    for (size_t k = 0; k < n; k++)
-        PCS_CUDA(launch_prove(b->digests, lg_sub, leaf_indices[k], o.u64() + k * lg_sub * 4, st));
+    PCS_CUDA(idx.alloc(n * 8, st));
+    PCS_CUDA(cudaMemcpyAsync(idx.p, leaf_indices, n * 8, cudaMemcpyHostToDevice, st));
+    PCS_CUDA(launch_prove_many(b->digests, lg_sub, idx.u64(), n, o.u64(), st));
     PCS_CUDA(cudaMemcpyAsync(siblings, o.p, n * lg_sub * 32, cudaMemcpyDeviceToHost, st));
     PCS_CUDA(cudaStreamSynchronize(st));
     return PCS_OK;

@@ -92,6 +92,8 @@ cudaError_t launch_two_to_one(const uint64_t* l, const uint64_t* r, size_t n, ui
 // Merkle path gather: siblings of leaf_index, bottom-up ([lg_sub][4]).
 cudaError_t launch_prove(const uint64_t* digests, unsigned lg_sub, size_t leaf_index, uint64_t* siblings,
                          cudaStream_t st);
+cudaError_t launch_prove_many(const uint64_t* digests, unsigned lg_sub, const uint64_t* leaf_indices_dev, size_t n,
+                              uint64_t* siblings, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // ntt.cu

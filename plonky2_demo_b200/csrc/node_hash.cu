@@ -68,6 +68,30 @@ cudaError_t launch_two_to_one(const uint64_t* l, const uint64_t* r, size_t n, ui
     return cudaGetLastError();
 }
 
+// The same for many leaves: block b copies the path of leaf_indices[b] to siblings[b][lg_sub][4].
+__global__ void k_prove_many(const uint64_t* __restrict__ digests, unsigned lg_sub, const uint64_t* __restrict__ leaf_indices,
+                             uint64_t* __restrict__ siblings) {
+    unsigned i = threadIdx.x;
+    if (i >= lg_sub) return;
+    size_t leaf_index = leaf_indices[blockIdx.x];
+    size_t s = leaf_index >> lg_sub;
+    size_t q = leaf_index & (((size_t)1 << lg_sub) - 1);
+    size_t node = (q >> i) ^ 1;
+    size_t sub_len = 2 * (((size_t)1 << lg_sub) - 1);
+    size_t idx = 2 * (((node >> 1) << (i + 1)) + ((size_t)1 << i) - 1) + (node & 1);
+    const uint64_t* src = digests + (s * sub_len + idx) * 4;
+    uint64_t* dst = siblings + ((size_t)blockIdx.x * lg_sub + i) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) dst[k] = src[k];
+}
+
+cudaError_t launch_prove_many(const uint64_t* digests, unsigned lg_sub, const uint64_t* leaf_indices_dev, size_t n,
+                              uint64_t* siblings, cudaStream_t st) {
+    if (lg_sub == 0 || n == 0) return cudaSuccess;
+    k_prove_many<<<(unsigned)n, 64, 0, st>>>(digests, lg_sub, leaf_indices_dev, siblings);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_prove(const uint64_t* digests, unsigned lg_sub, size_t leaf_index, uint64_t* siblings,
                          cudaStream_t st) {
     if (lg_sub == 0) return cudaSuccess;

@@ -90,10 +90,11 @@ def opening_proof(m, lg_d):
             and got.fri_query_indices == want["_indices"]
             and all(np.array_equal(s.evals, ws["evals"]) for r, wr in zip(got.query_round_proofs, want["query_round_proofs"])
                     for s, ws in zip(r.steps, wr["steps"])))
+    base_transcript = transcript(fp.Challenger)   # prove() has observed caps and openings before prove_openings starts
     rec = {"polys_at_zeta": len(all_polys), "polys_at_zeta_next": 2, "arities": params.reduction_arity_bits,
            "proof_equal_to_cpu_oracle": bool(same),
            "gpu_openings_ms": med(gpu_openings, 3),
-           "gpu_prove_openings_ms": med(lambda: fp.prove_openings(inst, gpu, transcript(fp.Challenger), params), 3),
+           "gpu_prove_openings_ms": med(lambda: fp.prove_openings(inst, gpu, base_transcript.clone(), params), 5),
            "cpu_oracle_prove_openings_ms": cpu_ms,
            "note": "CPU figure = oracle/fri.c arithmetic (OpenMP where the reference uses rayon) + Python protocol glue, one run"}
     for b in gpu:
