@@ -2,6 +2,7 @@
 // PolynomialBatch::from_coeffs / from_values path (plonky2/src/fri/oracle.rs:43-98) and the
 // accessors the reference's consumers need.  No CPU fallback anywhere in this file.
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -30,6 +31,11 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_sync = nullptr;
     std::vector<cudaEvent_t> chunk_ev;
+    // PAGEABLE host inputs (Rust Vecs, numpy arrays): gathered by a few host threads into a ring of pinned slots and
+    // sent with one DMA per slot; a plain cudaMemcpyAsync from pageable memory stages single-threaded inside the driver
+    void* ring[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ring_ev[3] = {nullptr, nullptr, nullptr};   // the DMA out of the slot has finished
+    bool ring_busy[3] = {false, false, false};
 };
 static Ctx g_ctx;
 
@@ -129,6 +135,10 @@ void pcs_shutdown(void) {
     if (g_ctx.pin_out) cudaFreeHost(g_ctx.pin_out);
     if (g_ctx.ev_sync) cudaEventDestroy(g_ctx.ev_sync);
     for (auto& e : g_ctx.chunk_ev) cudaEventDestroy(e);
+    for (auto& r : g_ctx.ring)
+        if (r) cudaFreeHost(r);
+    for (auto& e : g_ctx.ring_ev)
+        if (e) cudaEventDestroy(e);
     if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.stream);
     g_ctx = Ctx();
 }
@@ -312,6 +322,63 @@ static void* pinned(void*& buf, size_t& cap, size_t bytes) {
     return buf;
 }
 
+constexpr size_t RING_SLOT_BYTES = 16u << 20;
+constexpr unsigned STAGE_THREADS = 4;
+
+static bool is_pageable_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// copy stream bytes [off, off + len) of the concatenation polys[0] | polys[1] | ... (bytes_each each) to dst
+static void gather_bytes(char* dst, const uint64_t* const* polys, size_t bytes_each, size_t off, size_t len) {
+    while (len) {
+        size_t j = off / bytes_each, o = off % bytes_each;
+        size_t n = bytes_each - o < len ? bytes_each - o : len;
+        memcpy(dst, (const char*)polys[j] + o, n);
+        dst += n;
+        off += n;
+        len -= n;
+    }
+}
+
+// Send `count` pageable host polynomials (d elements each) to the contiguous device block `dst` through the pinned
+// ring: pieces of <= RING_SLOT_BYTES are gathered by STAGE_THREADS host threads and leave with one DMA each on the
+// copy stream; the gather of piece p + 1 overlaps the DMA of piece p.
+static int stage_pageable(const uint64_t* const* polys, size_t count, size_t d, uint64_t* dst, cudaStream_t copy_st) {
+    const size_t bytes_each = d * 8, total = count * bytes_each;
+    static unsigned next_slot = 0;
+    for (size_t off = 0; off < total; off += RING_SLOT_BYTES) {
+        const size_t len = total - off < RING_SLOT_BYTES ? total - off : RING_SLOT_BYTES;
+        const unsigned sl = next_slot++ % 3;
+        if (!g_ctx.ring[sl]) {
+            PCS_CUDA(cudaHostAlloc(&g_ctx.ring[sl], RING_SLOT_BYTES, cudaHostAllocDefault));
+            PCS_CUDA(cudaEventCreateWithFlags(&g_ctx.ring_ev[sl], cudaEventDisableTiming));
+        }
+        if (g_ctx.ring_busy[sl]) PCS_CUDA(cudaEventSynchronize(g_ctx.ring_ev[sl]));
+        char* slot = (char*)g_ctx.ring[sl];
+        const unsigned nt = len >= (1u << 20) ? STAGE_THREADS : 1;
+        if (nt == 1) {
+            gather_bytes(slot, polys, bytes_each, off, len);
+        } else {
+            std::thread th[STAGE_THREADS];
+            for (unsigned t = 0; t < nt; t++) {
+                size_t a = len * t / nt, e = len * (t + 1) / nt;
+                th[t] = std::thread(gather_bytes, slot + a, polys, bytes_each, off + a, e - a);
+            }
+            for (unsigned t = 0; t < nt; t++) th[t].join();
+        }
+        PCS_CUDA(cudaMemcpyAsync((char*)dst + off, slot, len, cudaMemcpyHostToDevice, copy_st));
+        PCS_CUDA(cudaEventRecord(g_ctx.ring_ev[sl], copy_st));
+        g_ctx.ring_busy[sl] = true;
+    }
+    return PCS_OK;
+}
+
 // gather w separately allocated host/device polynomials into one [w][d] device matrix
 static int stage_polys(const uint64_t* const* polys, size_t w, size_t d, bool device_ptrs, uint64_t* dst,
                        cudaStream_t st) {
@@ -481,8 +548,9 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
     DevBuf ptr_table;                // or: device table of the caller's w polynomial pointers, read in place
     uint64_t* staged = nullptr;
     bool scatter_coeffs = false;
-    constexpr size_t H2D_CHUNK = 16;  // polynomials per H2D chunk
+    size_t H2D_CHUNK = 16;            // polynomials per H2D chunk
     size_t n_chunks = 0;              // > 0: host inputs arrive chunk by chunk on the copy stream
+    bool pageable = false;            // ... through the pinned ring, each chunk staged right before its compute is enqueued
     if (contiguous_dev && !from_values && !(flags & PCS_KEEP_COEFFS)) {
         src = polys[0];
     } else if (dev_ptrs && !from_values && !(flags & PCS_KEEP_COEFFS) && lg_d >= 1) {
@@ -512,6 +580,11 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
             // host inputs: chunked H2D on the copy stream, one event per chunk
             if (!g_ctx.copy_stream) PCS_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
             if (!g_ctx.ev_sync) PCS_CUDA(cudaEventCreateWithFlags(&g_ctx.ev_sync, cudaEventDisableTiming));
+            for (size_t j = 0; j < w; j++)
+                if (!polys[j]) return fail(PCS_ERR_ARG, "NULL polynomial pointer");
+            pageable = w * d * 8 >= (8u << 20) && is_pageable_host(polys[0]);   // below 8 MB the threads cost more than they save
+            // pageable inputs: a chunk fills one ring slot, so that the staging threads are started once per 16 MB
+            if (pageable && H2D_CHUNK * d * 8 < RING_SLOT_BYTES) H2D_CHUNK = RING_SLOT_BYTES / (d * 8);
             n_chunks = (w + H2D_CHUNK - 1) / H2D_CHUNK;
             while (g_ctx.chunk_ev.size() < n_chunks) {
                 cudaEvent_t e;
@@ -520,7 +593,7 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
             }
             PCS_CUDA(cudaEventRecord(g_ctx.ev_sync, st));               // `staged` exists from here on
             PCS_CUDA(cudaStreamWaitEvent(g_ctx.copy_stream, g_ctx.ev_sync, 0));
-            for (size_t k = 0; k < n_chunks; k++) {
+            for (size_t k = 0; k < n_chunks && !pageable; k++) {
                 size_t j0 = k * H2D_CHUNK, j1 = j0 + H2D_CHUNK < w ? j0 + H2D_CHUNK : w;
                 int rc = stage_polys(polys + j0, j1 - j0, d, false, staged + j0 * d, g_ctx.copy_stream);
                 if (rc) {
@@ -560,6 +633,14 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
     if (chunked) {
         for (size_t k = 0; k < n_chunks; k++) {
             size_t j0 = k * H2D_CHUNK, j1 = j0 + H2D_CHUNK < w ? j0 + H2D_CHUNK : w;
+            if (pageable) {
+                int rc = stage_pageable(polys + j0, j1 - j0, d, staged + j0 * d, g_ctx.copy_stream);
+                if (rc) {
+                    cudaStreamSynchronize(g_ctx.copy_stream);
+                    return rc;
+                }
+                PCS_CUDA(cudaEventRecord(g_ctx.chunk_ev[k], g_ctx.copy_stream));
+            }
             PCS_CUDA(cudaStreamWaitEvent(st, g_ctx.chunk_ev[k], 0));
             if (from_values) {
                 int rc = ifft_range(j0, j1);
