@@ -30,6 +30,8 @@ from .fri_prover import (  # noqa: F401
     FriOracleInfo,
     FriPolynomialInfo,
     FriProof,
+    OpeningSet,
+    PlonkOpeningShape,
     eval_commitment,
     prove_openings,
 )
@@ -60,5 +62,5 @@ __all__ = [
     "FriConfig", "FriParams", "FriReductionStrategy", "PoseidonGoldilocksConfig", "PoseidonHash",
     "PoseidonPermutation", "HashOut", "CircuitConfig", "fft_with_options", "ifft_with_options",
     "verify_merkle_proof_to_cap", "Challenger", "FriInstanceInfo", "FriBatchInfo", "FriPolynomialInfo", "FriOracleInfo",
-    "FriProof", "ExtensionPolynomial", "eval_commitment", "prove_openings", "init", "shutdown", "synchronize", "PcsError",
+    "FriProof", "OpeningSet", "PlonkOpeningShape", "ExtensionPolynomial", "eval_commitment", "prove_openings", "init", "shutdown", "synchronize", "PcsError",
 ]

@@ -319,3 +319,74 @@ def prove_openings(instance, oracles, challenger, fri_params, timing=None):
 
 
 PolynomialBatch.prove_openings = staticmethod(prove_openings)
+
+
+# ---- the PLONK prover's use of the above (plonk/proof.rs:286-372, plonk/circuit_data.rs:431-595) ------------------------
+@dataclass
+class PlonkOpeningShape:
+    """The few numbers of CommonCircuitData that fix which polynomial is opened where (no lookups: the demo has none):
+    oracle 0 = constants + sigmas, 1 = wires, 2 = Zs + partial products, 3 = quotient chunks."""
+    degree_bits: int
+    num_constants: int
+    num_routed_wires: int
+    num_wires: int
+    num_challenges: int
+    num_partial_products: int
+    quotient_degree_factor: int
+
+    def constants_range(self):
+        return range(0, self.num_constants)                                            # circuit_data.rs:431-433
+
+    def sigmas_range(self):
+        return range(self.num_constants, self.num_constants + self.num_routed_wires)   # :436-438
+
+    def zs_range(self):
+        return range(0, self.num_challenges)                                           # :441-443
+
+    def partial_products_range(self):
+        return range(self.num_challenges, (self.num_partial_products + 1) * self.num_challenges)   # :446-448
+
+    def oracle_widths(self):
+        return [self.num_constants + self.num_routed_wires, self.num_wires,
+                self.num_challenges * (1 + self.num_partial_products), self.num_challenges * self.quotient_degree_factor]
+
+    def get_fri_instance(self, zeta):
+        """circuit_data.rs:461-481: everything at zeta, the Z polynomials also at g * zeta."""
+        g = primitive_root_of_unity(self.degree_bits)
+        widths = self.oracle_widths()
+        all_polys = [p for k, w in enumerate(widths) for p in FriPolynomialInfo.from_range(k, range(w))]   # fri_all_polys :586-595
+        return FriInstanceInfo(
+            oracles=[FriOracleInfo(w, False) for w in widths],
+            batches=[FriBatchInfo(zeta, all_polys),
+                     FriBatchInfo(ext_mul((g, 0), zeta), FriPolynomialInfo.from_range(2, self.zs_range()))])
+
+
+@dataclass
+class OpeningSet:
+    """plonk/proof.rs:286-304: the purported values of every committed polynomial at zeta (and of the Zs at g * zeta)."""
+    constants: np.ndarray
+    plonk_sigmas: np.ndarray
+    wires: np.ndarray
+    plonk_zs: np.ndarray
+    plonk_zs_next: np.ndarray
+    partial_products: np.ndarray
+    quotient_polys: np.ndarray
+
+    @classmethod
+    def new(cls, zeta, g, constants_sigmas_commitment, wires_commitment, zs_partial_products_commitment,
+            quotient_polys_commitment, shape):
+        """proof.rs:307-344: five batched evaluations on the device (eval_commitment), sliced by the ranges."""
+        cs = eval_commitment(zeta, constants_sigmas_commitment)
+        zs = eval_commitment(zeta, zs_partial_products_commitment)
+        zs_next = eval_commitment(ext_mul((int(g), 0), zeta), zs_partial_products_commitment)   # g: base-field generator
+        z0, z1 = shape.zs_range().start, shape.zs_range().stop
+        p0, p1 = shape.partial_products_range().start, shape.partial_products_range().stop
+        return cls(constants=cs[: shape.num_constants], plonk_sigmas=cs[shape.num_constants: shape.num_constants + shape.num_routed_wires],
+                   wires=eval_commitment(zeta, wires_commitment), plonk_zs=zs[z0:z1], plonk_zs_next=zs_next[z0:z1],
+                   partial_products=zs[p0:p1], quotient_polys=eval_commitment(zeta, quotient_polys_commitment))
+
+    def to_fri_openings(self):
+        """proof.rs:345-372 (no lookups): FriOpenings as two lists of extension values, in the instance's order."""
+        zeta_batch = np.concatenate([self.constants, self.plonk_sigmas, self.wires, self.plonk_zs, self.partial_products,
+                                     self.quotient_polys])
+        return [[(int(a), int(b)) for a, b in zeta_batch], [(int(a), int(b)) for a, b in self.plonk_zs_next]]

@@ -369,3 +369,42 @@ def test_serialize_device_batch_and_proof(pcs):
     assert back.pow_witness == proof.pow_witness and np.array_equal(back.final_poly, proof.final_poly)
     for b in gpu:
         b.free()
+
+
+def test_opening_set_and_plonk_instance(pcs):
+    """OpeningSet::new + get_fri_instance + prove_openings wired the way plonk/prover.rs:283-330 does it, on the m = 64
+    demo's oracle widths at a small degree; the restated verifier accepts."""
+    from plonky2_demo_b200.fri_prover import Challenger, OpeningSet, PlonkOpeningShape, prove_openings
+
+    lg_d = 7
+    shape = PlonkOpeningShape(degree_bits=lg_d, num_constants=4, num_routed_wires=80, num_wires=135, num_challenges=2,
+                              num_partial_products=9, quotient_degree_factor=8)
+    assert shape.oracle_widths() == [84, 135, 20, 16]
+    cfg = pcs.CircuitConfig.standard_recursion_config().fri_config
+    params = cfg.fri_params(lg_d, False)
+    coeffs = [seeded_polys(w, 1 << lg_d, 0x0511 + k) for k, w in enumerate(shape.oracle_widths())]
+    gpu = [pcs.PolynomialBatch.from_coeffs(c, cfg.rate_bits, False, cfg.cap_height, keep_coeffs=True) for c in coeffs]
+    zeta = (0x1234567 % P, 0x7654321 % P)
+    g = fr.primitive_root_of_unity(lg_d)
+    os_ = OpeningSet.new(zeta, g, *gpu, shape)
+    assert os_.constants.shape == (4, 2) and os_.plonk_sigmas.shape == (80, 2) and os_.plonk_zs_next.shape == (2, 2)
+    assert os_.partial_products.shape == (18, 2) and os_.quotient_polys.shape == (16, 2)
+    assert np.array_equal(os_.plonk_zs_next, fr.eval_base_polys_ext(coeffs[2][:2], fr.ext_mul((g, 0), zeta)))
+    inst = shape.get_fri_instance(zeta)
+    openings = os_.to_fri_openings()
+    assert len(openings[0]) == 255 and len(openings[1]) == 2
+    batches = [(b.point, [(p.oracle_index, p.polynomial_index) for p in b.polynomials]) for b in inst.batches]
+    ch = Challenger()
+    for b in gpu:
+        ch.observe_cap(b.merkle_tree.cap)
+    for vals in openings:
+        ch.observe_extension_elements(vals)
+    och = fr.Challenger()
+    och.sponge_state = [int(x) for x in ch.sponge_state.state]
+    och.input_buffer, och.output_buffer = list(ch.input_buffer), list(ch.output_buffer)
+    proof = prove_openings(inst, gpu, ch, params)
+    assert fr.verify_fri_proof(batches, openings, och, [b.merkle_tree.cap.hashes for b in gpu], _as_oracle_proof(proof),
+                               cfg.rate_bits, cfg.cap_height, params.reduction_arity_bits, cfg.proof_of_work_bits,
+                               cfg.num_query_rounds, lg_d)
+    for b in gpu:
+        b.free()
