@@ -408,3 +408,49 @@ def test_opening_set_and_plonk_instance(pcs):
                                cfg.num_query_rounds, lg_d)
     for b in gpu:
         b.free()
+
+
+def test_prove_openings_random_instances(pcs):
+    """30 seeded random instances: oracle counts and widths, degree, rate, cap height, arities (any split that leaves a
+    final polynomial), PoW bits, query counts, from_values / from_coeffs oracles.  GPU proof == oracle proof, verifier accepts."""
+    from plonky2_demo_b200.fri_prover import Challenger, eval_commitment, prove_openings
+
+    rng = random.Random(20261018)
+    for case in range(30):
+        lg_d = rng.randrange(0, 11)
+        rate_bits = rng.randrange(0, 4) if lg_d else rng.randrange(1, 4)
+        n_or = rng.randrange(1, 5)
+        widths = [rng.randrange(1, 12) for _ in range(n_or)]
+        arities, left = [], lg_d
+        while left > 0 and rng.random() < 0.7:
+            a = rng.randrange(1, min(4, left) + 1)
+            arities.append(a)
+            left -= a
+        # every tree needs cap_height <= log2(leaves) = lg_d + rate_bits - (arity bits so far) - arity
+        min_leaves_log = min([lg_d + rate_bits] + [lg_d + rate_bits - sum(arities[: i + 1]) for i in range(len(arities))])
+        cap_height = rng.randrange(0, min(min_leaves_log, 4) + 1)
+        pow_bits, n_q = rng.randrange(0, 9), rng.randrange(1, 6)
+        gpu, cpu, inst, batches = build_instance(pcs, lg_d, rate_bits, cap_height, widths, seed=1000 + case,
+                                                 from_values=bool(case & 1) and n_or > 1)
+        per_oracle = {pt: [eval_commitment(pt, b) for b in gpu] for pt, _ in batches}
+        openings = [[tuple(int(x) for x in per_oracle[pt][o][j]) for o, j in polys] for pt, polys in batches]
+        ch, och = Challenger(), fr.Challenger()
+        for c in (ch, och):
+            for o in cpu:
+                c.observe_cap(o["cap"])
+            for vals in openings:
+                c.observe_extension_elements(vals)
+        vch = och.clone()
+        cfg = pcs.FriConfig(rate_bits, cap_height, pow_bits, pcs.FriReductionStrategy.Fixed(arities), n_q)
+        params = cfg.fri_params(lg_d, False)
+        got = prove_openings(inst, gpu, ch, params)
+        want = fr.prove_openings(cpu, batches, och, rate_bits, cap_height, arities, pow_bits, n_q)
+        ctx = (case, lg_d, rate_bits, cap_height, arities, widths)
+        try:
+            _assert_same_proof(got, want)
+        except AssertionError as e:
+            raise AssertionError(f"case {ctx}: {e}")
+        assert fr.verify_fri_proof(batches, openings, vch, [o["cap"] for o in cpu], _as_oracle_proof(got), rate_bits,
+                                   cap_height, arities, pow_bits, n_q, lg_d), ctx
+        for b in gpu:
+            b.free()
