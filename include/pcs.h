@@ -171,6 +171,7 @@ PCS_API int pcs_batch_coeffs(const pcs_batch* b, size_t poly, uint64_t* coeffs /
 PCS_API int pcs_batch_all_coeffs(const pcs_batch* b, uint64_t* coeffs /*[w][d]*/);
 /* Device views (valid until pcs_batch_free): LDE is [leaf_len][N] poly-major in leaf order.        */
 PCS_API const uint64_t* pcs_batch_lde_dev(const pcs_batch* b);
+PCS_API const uint64_t* pcs_batch_coeffs_dev(const pcs_batch* b);   /* [w][d], or NULL when the coefficients were not kept */
 PCS_API const uint64_t* pcs_batch_digests_dev(const pcs_batch* b);
 PCS_API const uint64_t* pcs_batch_cap_dev(const pcs_batch* b);
 /* Wall-clock of the last commit's phases in ms, measured with CUDA events on pcs_stream():
@@ -193,6 +194,11 @@ PCS_API int pcs_timing_totals(float ms[5], unsigned* n_commits, int reset);
  *                                                                  plonky2/src/plonk/proof.rs:316-322          */
 PCS_API int pcs_batch_eval_ext(const pcs_batch* b, const uint64_t point[2], uint64_t* out /*[w][2]*/);
 
+/* The same for w polynomials given as DEVICE pointers (d = 2^lg_d coefficients each, anywhere in this GPU's memory):
+ * what a sharded commitment holds after its coefficient exchange, where no single batch owns them.        */
+PCS_API int pcs_eval_ext_dev(const uint64_t* const* polys_dev, size_t w, unsigned lg_d, const uint64_t point[2],
+                     uint64_t* out /*[w][2]*/);
+
 /* Device-resident PolynomialCoeffs<F::Extension> (coefficients of the polynomial FRI runs on).                       */
 typedef struct pcs_ext_poly pcs_ext_poly;
 PCS_API int pcs_ext_poly_new(const uint64_t* coeffs /*[len][2]*/, size_t len, pcs_ext_poly** out);
@@ -212,6 +218,12 @@ PCS_API int pcs_fri_final_poly(const pcs_batch* const* oracles, size_t n_oracles
                        const uint64_t* points /*[n_batches][2]*/, const size_t* batch_len,
                        const uint32_t* oracle_index, const uint32_t* poly_index, const uint64_t alpha[2],
                        pcs_ext_poly** out);
+
+/* The same with the instance's polynomials given directly as DEVICE pointers, batch after batch (sum of batch_len of
+ * them, d = 2^lg_d coefficients each).                                                                                */
+PCS_API int pcs_fri_final_poly_dev(const uint64_t* const* polys_dev, unsigned lg_d, size_t n_batches,
+                           const uint64_t* points /*[n_batches][2]*/, const size_t* batch_len, const uint64_t alpha[2],
+                           pcs_ext_poly** out);
 
 /* p.lde(rate_bits).coset_fft(shift.into()) of an extension polynomial: values in natural order, [len << rate_bits][2]
  * (`lde_final_values`, oracle.rs:202-207; the transform is F-linear, so it is the base-field coset LDE of both

@@ -48,6 +48,7 @@ SIGNATURES = {
     "pcs_batch_coeffs": (C.c_int, [C.c_void_p, sz, u64p]),
     "pcs_batch_all_coeffs": (C.c_int, [C.c_void_p, u64p]),
     "pcs_batch_lde_dev": (C.c_void_p, [C.c_void_p]),
+    "pcs_batch_coeffs_dev": (C.c_void_p, [C.c_void_p]),
     "pcs_batch_digests_dev": (C.c_void_p, [C.c_void_p]),
     "pcs_batch_cap_dev": (C.c_void_p, [C.c_void_p]),
     "pcs_batch_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
@@ -55,6 +56,8 @@ SIGNATURES = {
     "pcs_timing_totals": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_uint), C.c_int]),
     # FRI opening proof
     "pcs_batch_eval_ext": (C.c_int, [C.c_void_p, u64p, u64p]),
+    "pcs_eval_ext_dev": (C.c_int, [u64pp, sz, C.c_uint, u64p, u64p]),
+    "pcs_fri_final_poly_dev": (C.c_int, [u64pp, C.c_uint, sz, u64p, C.POINTER(sz), u64p, C.POINTER(C.c_void_p)]),
     "pcs_ext_poly_new": (C.c_int, [u64p, sz, C.POINTER(C.c_void_p)]),
     "pcs_ext_poly_len": (C.c_int, [C.c_void_p, C.POINTER(sz)]),
     "pcs_ext_poly_read": (C.c_int, [C.c_void_p, u64p]),

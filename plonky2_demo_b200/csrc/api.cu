@@ -917,6 +917,7 @@ int pcs_batch_all_coeffs(const pcs_batch* b, uint64_t* coeffs) {
 }
 
 const uint64_t* pcs_batch_lde_dev(const pcs_batch* b) { return b ? b->lde : nullptr; }
+const uint64_t* pcs_batch_coeffs_dev(const pcs_batch* b) { return b ? b->coeffs : nullptr; }
 const uint64_t* pcs_batch_digests_dev(const pcs_batch* b) { return b ? b->digests : nullptr; }
 const uint64_t* pcs_batch_cap_dev(const pcs_batch* b) { return b ? b->cap : nullptr; }
 

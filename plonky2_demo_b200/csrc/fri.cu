@@ -69,7 +69,8 @@ constexpr int EV_THREADS = 256, EV_PER_THREAD = 64, EV_BATCH = 16, EV_CHUNK = EV
 
 // grid (chunks, w).  Thread t of chunk c sums  coeff[c*16384 + t + 256 k] * (z^256)^k  over k < 64 carry-free (ext.cuh
 // lazy6, loads double-buffered in batches of 16), multiplies by z^t; the block adds its 256 partial sums and scales by z^(16384 c).
-__global__ void __launch_bounds__(EV_THREADS) k_eval_ext(const uint64_t* __restrict__ coeffs, size_t d,
+__global__ void __launch_bounds__(EV_THREADS) k_eval_ext(const uint64_t* __restrict__ coeffs,
+                                                         const uint64_t* const* __restrict__ poly_ptrs, size_t d,
                                                          const gl::ext2* __restrict__ pw_t /*[256] z^t*/,
                                                          const gl::ext2* __restrict__ pw_k /*[64] z^(256 k)*/,
                                                          const gl::ext2* __restrict__ pw_c /*[chunks] z^(16384 c)*/,
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_ext(const uint64_t* __restr
         s_k[t][4] = lb.w0; s_k[t][5] = lb.w1; s_k[t][6] = lb.w2; s_k[t][7] = 0;
     }
     __syncthreads();
-    const uint64_t* poly = coeffs + (size_t)blockIdx.y * d;
+    const uint64_t* poly = poly_ptrs ? poly_ptrs[blockIdx.y] : coeffs + (size_t)blockIdx.y * d;   // table: scattered polynomials
     const size_t base = (size_t)blockIdx.x * EV_CHUNK + t;
     gl::lazy6 A, B;   // 64 terms each: far below LAZY_MAX_TERMS
     gl::lazy_zero(A);
@@ -137,7 +138,8 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_ext(const uint64_t* __restr
 // (16384 coefficients); one elected thread streams it as bulk copies of 16 KB (8 k-steps) into a two-slot ring, each slot
 // completing on its own mbarrier, so 16-32 KB per block are in flight whatever the register budget.  Needs d % 256 == 0.
 constexpr int EV_GROUP = 8;                                   // k-steps (of 256 coefficients) per bulk copy
-__global__ void __launch_bounds__(EV_THREADS) k_eval_ext_tma(const uint64_t* __restrict__ coeffs, size_t d,
+__global__ void __launch_bounds__(EV_THREADS) k_eval_ext_tma(const uint64_t* __restrict__ coeffs,
+                                                             const uint64_t* const* __restrict__ poly_ptrs, size_t d,
                                                              const gl::ext2* __restrict__ pw_t, const gl::ext2* __restrict__ pw_k,
                                                              const gl::ext2* __restrict__ pw_c, gl::ext2* __restrict__ partial) {
     __shared__ __align__(128) uint64_t s_buf[2][EV_GROUP * EV_THREADS];   // 2 x 16 KB
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_ext_tma(const uint64_t* __r
         tma::fence_barrier_init();
     }
     __syncthreads();
-    const uint64_t* poly = coeffs + (size_t)blockIdx.y * d;
+    const uint64_t* poly = poly_ptrs ? poly_ptrs[blockIdx.y] : coeffs + (size_t)blockIdx.y * d;   // table: scattered polynomials
     const size_t base = (size_t)blockIdx.x * EV_CHUNK;
     const size_t left = d - base;                                            // > 0, multiple of 256
     const int n_steps = (int)(left < (size_t)EV_CHUNK ? left / EV_THREADS : EV_PER_THREAD);
@@ -510,14 +512,23 @@ int pow_table(glh::ext2 base, size_t n, gl::ext2* out, cudaStream_t st) {
 extern "C" {
 
 // ------------------------------------------------------------------------------------------------
-int pcs_batch_eval_ext(const pcs_batch* b, const uint64_t point[2], uint64_t* out) {
-    if (int rc = need_init()) return rc;
-    if (!b || !point || !out) return fail(PCS_ERR_ARG, "NULL pointer");
-    if (!b->coeffs) return fail(PCS_ERR_ARG, "coefficients were not kept (PCS_KEEP_COEFFS)");
+// coeffs: contiguous [w][d] device matrix, or (coeffs == nullptr) polys: HOST array of w device pointers
+static int eval_ext_common(const uint64_t* coeffs, const uint64_t* const* polys, size_t w, unsigned lg_d,
+                           const uint64_t point[2], uint64_t* out) {
     cudaStream_t st = (cudaStream_t)pcs_stream();
-    const size_t d = (size_t)1 << b->lg_d, w = b->w, chunks = (d + EV_CHUNK - 1) / EV_CHUNK;
+    const size_t d = (size_t)1 << lg_d, chunks = (d + EV_CHUNK - 1) / EV_CHUNK;
     glh::ext2 z = {point[0] % glh::P, point[1] % glh::P};
-    DevBuf tabs, partial, res;
+    DevBuf tabs, partial, res, table;
+    bool aligned = true;
+    if (!coeffs) {
+        for (size_t j = 0; j < w; j++) {
+            if (!polys[j]) return fail(PCS_ERR_ARG, "NULL polynomial pointer");
+            aligned = aligned && ((uintptr_t)polys[j] % 16 == 0);
+        }
+        PCS_CUDA(table.alloc(w * sizeof(uint64_t*), st));
+        PCS_CUDA(cudaMemcpyAsync(table.p, polys, w * sizeof(uint64_t*), cudaMemcpyHostToDevice, st));
+    }
+    const uint64_t* const* ptrs = coeffs ? nullptr : (const uint64_t* const*)table.p;
     PCS_CUDA(tabs.alloc((EV_THREADS + EV_PER_THREAD + chunks) * sizeof(gl::ext2), st));
     PCS_CUDA(partial.alloc(w * chunks * sizeof(gl::ext2), st));
     PCS_CUDA(res.alloc(w * 16, st));
@@ -528,11 +539,11 @@ int pcs_batch_eval_ext(const pcs_batch* b, const uint64_t point[2], uint64_t* ou
     if ((rc = pow_table(z, EV_THREADS, pw_t, st))) return rc;
     if ((rc = pow_table(glh::ext_pow(z, EV_THREADS), EV_PER_THREAD, pw_k, st))) return rc;
     if ((rc = pow_table(glh::ext_pow(z, EV_CHUNK), chunks, pw_c, st))) return rc;
-    if (d % EV_THREADS == 0)   // TMA-staged (rows of a [w][d] matrix with d >= 256 are 16-byte aligned)
-        k_eval_ext_tma<<<dim3((unsigned)chunks, (unsigned)w), EV_THREADS, 0, st>>>(b->coeffs, d, pw_t, pw_k, pw_c,
+    if (d % EV_THREADS == 0 && aligned)   // TMA-staged (rows of a [w][d] matrix with d >= 256 are 16-byte aligned)
+        k_eval_ext_tma<<<dim3((unsigned)chunks, (unsigned)w), EV_THREADS, 0, st>>>(coeffs, ptrs, d, pw_t, pw_k, pw_c,
                                                                                    (gl::ext2*)partial.p);
     else
-        k_eval_ext<<<dim3((unsigned)chunks, (unsigned)w), EV_THREADS, 0, st>>>(b->coeffs, d, pw_t, pw_k, pw_c,
+        k_eval_ext<<<dim3((unsigned)chunks, (unsigned)w), EV_THREADS, 0, st>>>(coeffs, ptrs, d, pw_t, pw_k, pw_c,
                                                                                (gl::ext2*)partial.p);
     PCS_CUDA(cudaGetLastError());
     k_eval_sum<<<(unsigned)w, 256, 0, st>>>((const gl::ext2*)partial.p, chunks, res.u64());
@@ -540,6 +551,21 @@ int pcs_batch_eval_ext(const pcs_batch* b, const uint64_t point[2], uint64_t* ou
     PCS_CUDA(cudaMemcpyAsync(out, res.p, w * 16, cudaMemcpyDeviceToHost, st));
     PCS_CUDA(cudaStreamSynchronize(st));
     return PCS_OK;
+}
+
+int pcs_batch_eval_ext(const pcs_batch* b, const uint64_t point[2], uint64_t* out) {
+    if (int rc = need_init()) return rc;
+    if (!b || !point || !out) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (!b->coeffs) return fail(PCS_ERR_ARG, "coefficients were not kept (PCS_KEEP_COEFFS)");
+    return eval_ext_common(b->coeffs, nullptr, b->w, b->lg_d, point, out);
+}
+
+int pcs_eval_ext_dev(const uint64_t* const* polys_dev, size_t w, unsigned lg_d, const uint64_t point[2], uint64_t* out) {
+    if (int rc = need_init()) return rc;
+    if (w == 0) return PCS_OK;
+    if (!polys_dev || !point || !out) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (lg_d > 32) return fail(PCS_ERR_TWO_ADICITY, "n_log <= TWO_ADICITY violated");
+    return eval_ext_common(nullptr, polys_dev, w, lg_d, point, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -611,35 +637,15 @@ void pcs_ext_poly_free(pcs_ext_poly* p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-int pcs_fri_final_poly(const pcs_batch* const* oracles, size_t n_oracles, size_t n_batches, const uint64_t* points,
-                       const size_t* batch_len, const uint32_t* oracle_index, const uint32_t* poly_index,
-                       const uint64_t alpha[2], pcs_ext_poly** out) {
-    if (int rc = need_init()) return rc;
-    if (!out) return fail(PCS_ERR_ARG, "out is NULL");
-    *out = nullptr;
-    if (!oracles || !n_oracles || !n_batches || !points || !batch_len || !oracle_index || !poly_index || !alpha)
-        return fail(PCS_ERR_ARG, "NULL pointer or empty instance");
-    for (size_t o = 0; o < n_oracles; o++) {
-        if (!oracles[o]) return fail(PCS_ERR_ARG, "NULL oracle");
-        if (!oracles[o]->coeffs) return fail(PCS_ERR_ARG, "coefficients were not kept (PCS_KEEP_COEFFS)");
-        if (oracles[o]->lg_d != oracles[0]->lg_d) return fail(PCS_ERR_ARG, "oracles of different degrees");
-    }
+// ptrs: `total` device pointers to d = 2^lg_d coefficients each, batch after batch
+static int final_poly_common(const std::vector<const uint64_t*>& ptrs, unsigned lg_d, size_t n_batches, const uint64_t* points,
+                             const size_t* batch_len, const uint64_t alpha[2], pcs_ext_poly** out) {
     cudaStream_t st = (cudaStream_t)pcs_stream();
-    const unsigned lg_d = oracles[0]->lg_d;
-    const size_t d = (size_t)1 << lg_d;
-    size_t total = 0, longest = 0;
-    for (size_t i = 0; i < n_batches; i++) {
-        if (batch_len[i] == 0) return fail(PCS_ERR_ARG, "empty FRI batch");
-        total += batch_len[i];
-        longest = batch_len[i] > longest ? batch_len[i] : longest;
-    }
-    std::vector<const uint64_t*> ptrs(total);
-    for (size_t k = 0; k < total; k++) {
-        if (oracle_index[k] >= n_oracles) return fail(PCS_ERR_ARG, "oracle index out of bounds");
-        const pcs_batch* o = oracles[oracle_index[k]];
-        if (poly_index[k] >= o->w) return fail(PCS_ERR_ARG, "polynomial index out of bounds");
-        ptrs[k] = o->coeffs + (size_t)poly_index[k] * d;
-    }
+    const size_t d = (size_t)1 << lg_d, total = ptrs.size();
+    size_t longest = 0;
+    bool aligned = true;
+    for (size_t i = 0; i < n_batches; i++) longest = batch_len[i] > longest ? batch_len[i] : longest;
+    for (auto q : ptrs) aligned = aligned && ((uintptr_t)q % 16 == 0);
     const glh::ext2 a = {alpha[0] % glh::P, alpha[1] % glh::P};
     pcs_ext_poly* fin = nullptr;
     int rc = ext_poly_alloc(d, &fin, st);
@@ -655,7 +661,7 @@ int pcs_fri_final_poly(const pcs_batch* const* oracles, size_t n_oracles, size_t
     size_t first = 0;
     for (size_t i = 0; i < n_batches; i++) {
         const size_t m = batch_len[i];
-        if (d % RT_COLS == 0)   // TMA-staged
+        if (d % RT_COLS == 0 && aligned)   // TMA-staged
             k_reduce_polys_base_tma<<<(unsigned)(d / RT_COLS), RT_COLS, 0, st>>>(
                 (const uint64_t* const*)table.p + first, m, (const gl::ext2*)apow.p, d, comp.u64(), d);
         else
@@ -673,6 +679,54 @@ int pcs_fri_final_poly(const pcs_batch* const* oracles, size_t n_oracles, size_t
     guard.armed = false;
     *out = fin;
     return PCS_OK;
+}
+
+int pcs_fri_final_poly(const pcs_batch* const* oracles, size_t n_oracles, size_t n_batches, const uint64_t* points,
+                       const size_t* batch_len, const uint32_t* oracle_index, const uint32_t* poly_index,
+                       const uint64_t alpha[2], pcs_ext_poly** out) {
+    if (int rc = need_init()) return rc;
+    if (!out) return fail(PCS_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!oracles || !n_oracles || !n_batches || !points || !batch_len || !oracle_index || !poly_index || !alpha)
+        return fail(PCS_ERR_ARG, "NULL pointer or empty instance");
+    for (size_t o = 0; o < n_oracles; o++) {
+        if (!oracles[o]) return fail(PCS_ERR_ARG, "NULL oracle");
+        if (!oracles[o]->coeffs) return fail(PCS_ERR_ARG, "coefficients were not kept (PCS_KEEP_COEFFS)");
+        if (oracles[o]->lg_d != oracles[0]->lg_d) return fail(PCS_ERR_ARG, "oracles of different degrees");
+    }
+    const unsigned lg_d = oracles[0]->lg_d;
+    const size_t d = (size_t)1 << lg_d;
+    size_t total = 0;
+    for (size_t i = 0; i < n_batches; i++) {
+        if (batch_len[i] == 0) return fail(PCS_ERR_ARG, "empty FRI batch");
+        total += batch_len[i];
+    }
+    std::vector<const uint64_t*> ptrs(total);
+    for (size_t k = 0; k < total; k++) {
+        if (oracle_index[k] >= n_oracles) return fail(PCS_ERR_ARG, "oracle index out of bounds");
+        const pcs_batch* o = oracles[oracle_index[k]];
+        if (poly_index[k] >= o->w) return fail(PCS_ERR_ARG, "polynomial index out of bounds");
+        ptrs[k] = o->coeffs + (size_t)poly_index[k] * d;
+    }
+    return final_poly_common(ptrs, lg_d, n_batches, points, batch_len, alpha, out);
+}
+
+int pcs_fri_final_poly_dev(const uint64_t* const* polys_dev, unsigned lg_d, size_t n_batches, const uint64_t* points,
+                           const size_t* batch_len, const uint64_t alpha[2], pcs_ext_poly** out) {
+    if (int rc = need_init()) return rc;
+    if (!out) return fail(PCS_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!polys_dev || !n_batches || !points || !batch_len || !alpha) return fail(PCS_ERR_ARG, "NULL pointer or empty instance");
+    if (lg_d > 32) return fail(PCS_ERR_TWO_ADICITY, "n_log <= TWO_ADICITY violated");
+    size_t total = 0;
+    for (size_t i = 0; i < n_batches; i++) {
+        if (batch_len[i] == 0) return fail(PCS_ERR_ARG, "empty FRI batch");
+        total += batch_len[i];
+    }
+    std::vector<const uint64_t*> ptrs(polys_dev, polys_dev + total);
+    for (auto q : ptrs)
+        if (!q) return fail(PCS_ERR_ARG, "NULL polynomial pointer");
+    return final_poly_common(ptrs, lg_d, n_batches, points, batch_len, alpha, out);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -224,10 +224,30 @@ class ExtensionPolynomial:
 
 
 # ---- openings (plonk/proof.rs:316-322) ----------------------------------------------------------------------------
+def _order_after_torch(batch):
+    """A sharded batch's collectives complete on torch's stream: make the engine's stream wait for them."""
+    eng = getattr(batch, "engine", None)
+    if eng is not None and hasattr(eng, "_order_after_torch"):
+        eng._order_after_torch()
+
+
+def _poly_ptr_array(addresses):
+    arr = (_ffi.u64p * len(addresses))()
+    for i, a in enumerate(addresses):
+        arr[i] = C.cast(C.c_void_p(int(a)), _ffi.u64p)
+    return arr
+
+
 def eval_commitment(z, batch):
-    """c.polynomials.par_iter().map(|p| p.to_extension().eval(z)) -> [w][2], on the device."""
+    """c.polynomials.par_iter().map(|p| p.to_extension().eval(z)) -> [w][2], on the device.  `batch`: a PolynomialBatch, or a
+    ShardedPolynomialBatch (every rank holds every coefficient after the exchange and evaluates all of them)."""
     out = np.empty((batch.n_polys, 2), dtype=np.uint64)
-    _ffi.check(_ffi.lib().pcs_batch_eval_ext(batch._h, _ext_arg(z), _ffi.ptr(out)))
+    if hasattr(batch, "poly_device_ptrs"):
+        _order_after_torch(batch)
+        ptrs = _poly_ptr_array(batch.poly_device_ptrs())
+        _ffi.check(_ffi.lib().pcs_eval_ext_dev(ptrs, batch.n_polys, batch.degree_log, _ext_arg(z), _ffi.ptr(out)))
+    else:
+        _ffi.check(_ffi.lib().pcs_batch_eval_ext(batch._h, _ext_arg(z), _ffi.ptr(out)))
     return out
 
 
@@ -239,8 +259,26 @@ def final_poly(instance, oracles, alpha):
     lens = (C.c_size_t * len(instance.batches))(*[len(b.polynomials) for b in instance.batches])
     oi = np.fromiter((p.oracle_index for b in instance.batches for p in b.polynomials), dtype=np.uint32, count=total)
     pi = np.fromiter((p.polynomial_index for b in instance.batches for p in b.polynomials), dtype=np.uint32, count=total)
-    handles = (C.c_void_p * len(oracles))(*[o._h for o in oracles])
     h = C.c_void_p()
+    if any(hasattr(o, "poly_device_ptrs") for o in oracles):
+        # sharded commitments: the coefficients live in the exchange buffers, not in a batch -> address them directly
+        per_oracle = []
+        for o in oracles:
+            if hasattr(o, "poly_device_ptrs"):
+                _order_after_torch(o)
+                per_oracle.append(o.poly_device_ptrs())
+            else:
+                base = _ffi.lib().pcs_batch_coeffs_dev(o._h)
+                if not base:
+                    raise _ffi.PcsError(-5, "coefficients were not kept (PCS_KEEP_COEFFS)")
+                per_oracle.append([base + 8 * (j << o.degree_log) for j in range(o.n_polys)])
+        if len({o.degree_log for o in oracles}) != 1:
+            raise _ffi.PcsError(-5, "oracles of different degrees")
+        ptrs = _poly_ptr_array([per_oracle[int(o)][int(j)] for o, j in zip(oi, pi)])
+        _ffi.check(_ffi.lib().pcs_fri_final_poly_dev(ptrs, oracles[0].degree_log, len(instance.batches), _ffi.ptr(points),
+                                                     lens, _ext_arg(alpha), C.byref(h)))
+        return ExtensionPolynomial(h)
+    handles = (C.c_void_p * len(oracles))(*[o._h for o in oracles])
     _ffi.check(_ffi.lib().pcs_fri_final_poly(handles, len(oracles), len(instance.batches), _ffi.ptr(points), lens,
                                              oi.ctypes.data_as(C.POINTER(C.c_uint32)),
                                              pi.ctypes.data_as(C.POINTER(C.c_uint32)), _ext_arg(alpha), C.byref(h)))
@@ -308,7 +346,13 @@ def fri_proof(initial_merkle_trees, poly, challenger, fri_params):
 
 def prove_openings(instance, oracles, challenger, fri_params, timing=None):
     """PolynomialBatch::prove_openings (oracle.rs:162-219): a batch opening proof for `instance` over the committed
-    `oracles` (which must hold their coefficients on the device: from_values, or from_coeffs(keep_coeffs=True))."""
+    `oracles` (which must hold their coefficients on the device: from_values, or from_coeffs(keep_coeffs=True)).
+
+    The oracles may be ShardedPolynomialBatch objects (one commitment spread over several GPUs): the call is
+    then COLLECTIVE.  Every rank holds every coefficient after the commit's exchange and runs the same deterministic
+    transcript, final polynomial, commit-phase trees and folds (they are 1/135th of the commitment's work, so they are
+    replicated rather than sharded); only the query phase communicates: the rows and Merkle paths of the sharded initial
+    trees are fetched from the rank that owns the leaf.  Every rank returns the same FriProof."""
     alpha = challenger.get_extension_challenge()
     poly = final_poly(instance, oracles, alpha)
     assert len(poly) == 1 << fri_params.degree_bits

@@ -454,6 +454,24 @@ class ShardedPolynomialBatch:
 
         return MerkleProof(sib)
 
+    def prove_many(self, leaf_indices):
+        """MerkleTree::prove for several global leaf indices (collective; the FRI query phase, fri/prover.rs:162-216)."""
+        return [self.prove(int(i)) for i in leaf_indices]
+
+    def poly_device_ptrs(self):
+        """Device address of every polynomial's coefficient vector on THIS rank (PolynomialBatch.polynomials, replicated by
+        the coefficient exchange): what the opening proof reads (fri_prover.eval_commitment / final_poly)."""
+        d = 1 << self.degree_log
+        if isinstance(self._coeffs, list):          # streaming exchange: chunk c holds its polynomials in rows [0, len_c)
+            ptrs = []
+            for c, (g, _mine) in enumerate(self._coeffs):
+                lo, hi = self.plan.chunk_range(c)
+                ptrs += [g.data_ptr() + 8 * d * i for i in range(hi - lo)]
+            return ptrs
+        if self._coeffs is None or self._coeffs.shape[0] < self.n_polys:
+            raise ValueError("this rank does not hold every polynomial's coefficients (exchange='peer' keeps only its block)")
+        return [self._coeffs.data_ptr() + 8 * d * j for j in range(self.n_polys)]
+
     def free(self):
         if self._h is not None:
             self.engine.free(self._h)

@@ -334,3 +334,66 @@ def test_cuda_intt_dev_matches_oracle():
     CudaShardEngine().intt_local(t)
     p.synchronize()
     assert np.array_equal(t.cpu().numpy().view(np.uint64), oracle.fft(vals, inverse=True))
+
+
+# ---------------------------------------------------------------------------------------------
+# opening proof over sharded commitments (world = 1 here; tests/harness/sharded_opening_check.py runs it on 2+ GPUs)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunks", [1, 3])
+def test_cuda_opening_proof_over_sharded_oracles(chunks):
+    import torch
+
+    import plonky2_demo_b200 as p
+    from oracle import fri_ref as fr
+    from plonky2_demo_b200 import fri_prover as fp
+    from plonky2_demo_b200.sharded import ShardedPolynomialBatch
+
+    p.init(0)
+    lg_d, r, cap, widths = 9, 2, 2, [7, 12, 3]
+    coeffs = [seeded_polys(w, 1 << lg_d, base_seed=77 + k) for k, w in enumerate(widths)]
+    plain = [p.PolynomialBatch.from_coeffs(c, r, False, cap, keep_coeffs=True) for c in coeffs]
+    # chunks > 1 only takes effect with a process group; world == 1 exercises the single-tensor layout either way
+    sharded = [ShardedPolynomialBatch.from_coeffs(torch.from_numpy(c.view(np.int64).copy()).cuda(), c.shape[0], r, cap,
+                                                  partitioned=False, chunks=chunks) for c in coeffs]
+    for a, b in zip(plain, sharded):
+        assert np.array_equal(a.merkle_tree.cap.hashes, b.cap)
+    zeta = (123456789, 987654321)
+    for a, b, c in zip(plain, sharded, coeffs):
+        want = fr.eval_base_polys_ext(c, zeta)
+        assert np.array_equal(fp.eval_commitment(zeta, a), want)
+        assert np.array_equal(fp.eval_commitment(zeta, b), want)
+    all_polys = [(k, j) for k, w in enumerate(widths) for j in range(w)]
+    zeta_next = fr.ext_mul((fr.primitive_root_of_unity(lg_d), 0), zeta)
+    batches = [(zeta, all_polys), (zeta_next, [(2, 0), (2, 1)])]
+    inst = fp.FriInstanceInfo([fp.FriOracleInfo(w, False) for w in widths],
+                              [fp.FriBatchInfo(pt, [fp.FriPolynomialInfo(o, j) for o, j in polys]) for pt, polys in batches])
+    cfg = p.FriConfig(r, cap, 6, p.FriReductionStrategy.Fixed([3, 2]), 5)
+    params = cfg.fri_params(lg_d, False)
+
+    def transcript():
+        ch = fp.Challenger()
+        for b in sharded:
+            ch.observe_cap(b.cap)
+        return ch
+
+    alpha = (5, 6)
+    f1, f2 = fp.final_poly(inst, plain, alpha), fp.final_poly(inst, sharded, alpha)
+    mixed = fp.final_poly(inst, [plain[0], sharded[1], plain[2]], alpha)
+    want = fr.final_poly(coeffs, batches, alpha)
+    assert np.array_equal(f1.coeffs, want) and np.array_equal(f2.coeffs, want) and np.array_equal(mixed.coeffs, want)
+    pa = fp.prove_openings(inst, plain, transcript(), params)
+    pb = fp.prove_openings(inst, sharded, transcript(), params)
+    assert pa.pow_witness == pb.pow_witness and pa.fri_query_indices == pb.fri_query_indices
+    assert np.array_equal(pa.final_poly, pb.final_poly)
+    for ca, cb in zip(pa.commit_phase_merkle_caps, pb.commit_phase_merkle_caps):
+        assert ca == cb
+    for ra, rb in zip(pa.query_round_proofs, pb.query_round_proofs):
+        for (va, ma), (vb, mb) in zip(ra.initial_trees_proof.evals_proofs, rb.initial_trees_proof.evals_proofs):
+            assert np.array_equal(va, vb) and np.array_equal(ma.siblings, mb.siblings)
+        for sa, sb in zip(ra.steps, rb.steps):
+            assert np.array_equal(sa.evals, sb.evals) and np.array_equal(sa.merkle_proof.siblings, sb.merkle_proof.siblings)
+    for b in plain + sharded:
+        b.free()
+    for f in (f1, f2, mixed):
+        f.free()
