@@ -36,6 +36,9 @@ def main():
     ap.add_argument("--from-values", action="store_true",
                     help="start from point values: each rank IFFTs its own polynomials on its GPU (pcs_ntt_dev), then the sharded from_coeffs")
     ap.add_argument("--eval-polys", type=int, default=4, help="polynomials evaluated directly on the CPU per sampled leaf")
+    ap.add_argument("--opening", action="store_true",
+                    help="also run the opening proof over the sharded commitment (all polynomials at zeta, 20 at g*zeta, "
+                         "standard_recursion_config) and have the restated verifier check it")
     a = ap.parse_args()
 
     import torch
@@ -112,6 +115,66 @@ def main():
             ok_rows &= int(rows[k][mine[j]]) == oracle.poly_eval(host[j], x)
     flag = torch.tensor([int(ok_rows)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    opening = None
+    if a.opening:
+        from oracle import fri_ref as fr
+        from plonky2_demo_b200 import fri_prover as fp
+
+        base_cfg = pcs.CircuitConfig.standard_recursion_config().fri_config
+        cfg = pcs.FriConfig(r, cap_h, base_cfg.proof_of_work_bits, base_cfg.reduction_strategy, base_cfg.num_query_rounds)
+        params = cfg.fri_params(lg_d, False)
+        zeta = (0x0123456789ABCDEF % fp.P, 0x0FEDCBA987654321 % fp.P)
+        zeta_next = fp.ext_mul((fp.primitive_root_of_unity(lg_d), 0), zeta)
+        n_next = min(20, w)
+        batches = [(zeta, [(0, j) for j in range(w)]), (zeta_next, [(0, j) for j in range(n_next)])]
+        inst = fp.FriInstanceInfo([fp.FriOracleInfo(w, False)],
+                                  [fp.FriBatchInfo(pt, [fp.FriPolynomialInfo(o, j) for o, j in polys]) for pt, polys in batches])
+
+        def timed(f):
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = f()
+            torch.cuda.synchronize()
+            tt = torch.tensor([1e3 * (time.perf_counter() - t0)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return out, float(tt.item())
+
+        at_zeta, eval_ms = timed(lambda: fp.eval_commitment(zeta, batch))
+        at_next = fp.eval_commitment(zeta_next, batch)
+        openings = [[tuple(int(x) for x in at_zeta[j]) for j in range(w)], [tuple(int(x) for x in at_next[j]) for j in range(n_next)]]
+
+        def transcript(cls):
+            ch = cls()
+            ch.observe_cap(batch.cap)
+            for vals in openings:
+                ch.observe_extension_elements(vals)
+            return ch
+
+        base = transcript(fp.Challenger)
+        proof, prove_ms = timed(lambda: fp.prove_openings(inst, [batch], base.clone(), params))
+        opening = {"arities": params.reduction_arity_bits, "queries": cfg.num_query_rounds, "pow_bits": cfg.proof_of_work_bits,
+                   "eval_commitment_ms": eval_ms, "prove_openings_ms": prove_ms, "final_poly_len": int(proof.final_poly.shape[0])}
+        if rank == 0:
+            as_oracle = {
+                "commit_phase_merkle_caps": [c.hashes for c in proof.commit_phase_merkle_caps], "final_poly": proof.final_poly,
+                "pow_witness": proof.pow_witness,
+                "query_round_proofs": [
+                    {"initial_trees_proof": [(ev, np.asarray(mp.siblings).reshape(-1, 4)) for ev, mp in rr.initial_trees_proof.evals_proofs],
+                     "steps": [{"evals": s.evals, "merkle_proof": np.asarray(s.merkle_proof.siblings).reshape(-1, 4)} for s in rr.steps]}
+                    for rr in proof.query_round_proofs]}
+            # the verifier re-derives every challenge from the same transcript and checks the openings against the cap
+            opening["verifier_accepts"] = bool(fr.verify_fri_proof(
+                batches, openings, transcript(fr.Challenger), [batch.cap], as_oracle, r, cap_h, params.reduction_arity_bits,
+                cfg.proof_of_work_bits, cfg.num_query_rounds, lg_d))
+            bad = [list(v) for v in openings]
+            bad[0][3] = ((bad[0][3][0] + 1) % fp.P, bad[0][3][1])
+            try:
+                fr.verify_fri_proof(batches, bad, transcript(fr.Challenger), [batch.cap], as_oracle, r, cap_h,
+                                    params.reduction_arity_bits, cfg.proof_of_work_bits, cfg.num_query_rounds, lg_d)
+                opening["wrong_opening_rejected"] = False
+            except AssertionError:
+                opening["wrong_opening_rejected"] = True
     if rank == 0:
         elems = w * n
         best = min(times)
@@ -121,7 +184,7 @@ def main():
             "ms": times, "best_ms": best, "elems_per_s": elems / (best * 1e-3), "lde_bytes": elems * 8,
             "sampled_leaves": leaves, "merkle_paths_verify_against_cap": bool(ok_paths),
             "rows_equal_direct_cpu_evaluation": bool(flag.item()), "polys_evaluated_per_rank": min(a.eval_polys, len(mine)),
-            "input_generation_s": gen_s, "cap0": [hex(int(v)) for v in batch.cap[0]]}))
+            "input_generation_s": gen_s, "cap0": [hex(int(v)) for v in batch.cap[0]], "opening_proof": opening}))
     batch.free()
     dist.barrier()
     dist.destroy_process_group()
