@@ -416,9 +416,9 @@ __global__ void k_seg_horner(const uint64_t* __restrict__ c, size_t c_stride, si
     h[h_stride + s] = gl::canon(acc.b);
 }
 
-__global__ void k_seg_scan(const uint64_t* __restrict__ c, size_t c_stride, size_t n, gl::ext2 z,
-                           const uint64_t* __restrict__ carry, size_t carry_stride, uint64_t* e, size_t e_stride,
-                           size_t n_seg) {
+// (no __restrict__: the scan runs in place, e == c, and the carries may live in the buffer being scanned one level up)
+__global__ void k_seg_scan(const uint64_t* c, size_t c_stride, size_t n, gl::ext2 z, const uint64_t* carry,
+                           size_t carry_stride, uint64_t* e, size_t e_stride, size_t n_seg) {
     size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seg) return;
     size_t lo = s * SEG, hi = lo + SEG < n ? lo + SEG : n;
