@@ -131,3 +131,25 @@ def test_bench_reference_arm_prints_one_json_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
                           "--cpu-sample-lg-d", "8"], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_rust_sys_binding_is_generated_from_header(built_lib):
+    """rust/pcs-sys/src/lib.rs is what tools/gen_rust_sys.py makes of include/pcs.h, and declares exactly the exported symbols."""
+    import importlib.util
+    import re
+
+    spec = importlib.util.spec_from_file_location("gen_rust_sys", os.path.join(ROOT, "tools", "gen_rust_sys.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    with open(os.path.join(ROOT, "rust", "pcs-sys", "src", "lib.rs")) as f:
+        committed = f.read()
+    assert committed == gen.generate(), "run `python tools/gen_rust_sys.py` after changing include/pcs.h"
+    rust_fns = set(re.findall(r"pub fn (pcs_\w+)\(", committed))
+    import plonky2_demo_b200 as p
+
+    assert rust_fns == set(p.SIGNATURES), rust_fns ^ set(p.SIGNATURES)
+    # pointer constness survives the translation (spot checks against the header)
+    assert "coeffs_out: *const *mut u64" in committed            # uint64_t* const* coeffs_out
+    assert "polys: *const *const u64" in committed               # const uint64_t* const* polys
+    assert "out: *mut *mut pcs_batch" in committed               # pcs_batch** out
+    assert "pub fn pcs_last_error() -> *const c_char;" in committed
