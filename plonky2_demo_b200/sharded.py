@@ -455,8 +455,29 @@ class ShardedPolynomialBatch:
         return MerkleProof(sib)
 
     def prove_many(self, leaf_indices):
-        """MerkleTree::prove for several global leaf indices (collective; the FRI query phase, fri/prover.rs:162-216)."""
-        return [self.prove(int(i)) for i in leaf_indices]
+        """MerkleTree::prove for several global leaf indices in ONE collective (the FRI query phase, fri/prover.rs:162-216):
+        every rank fills in the paths of the leaves it owns, a sum all-reduce (disjoint owners) replicates them."""
+        import torch
+        import torch.distributed as dist
+        from .hashing import MerkleProof
+
+        plan = self.plan
+        idx = [int(i) for i in leaf_indices]
+        n_local = log2_strict(plan.local_leaves) - plan.local_cap_height
+        n_total = n_local + plan.top_levels
+        sib = np.zeros((len(idx), n_total, 4), dtype=np.uint64)
+        for k, leaf in enumerate(idx):
+            owner = plan.owner_of_leaf(leaf)
+            if owner != self.rank:
+                continue
+            local = self.engine.prove(self._h, leaf - plan.leaf_range(owner)[0], n_local) if n_local else np.zeros((0, 4), np.uint64)
+            sib[k] = plan.extend_proof(owner, local, self._local_caps.reshape(self.world, -1, 4)[:, 0], self.engine.two_to_one) \
+                if plan.top_levels else local
+        if self.world > 1 and sib.size:
+            t = torch.from_numpy(sib.view(np.int64)).to(self._device())
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            sib = t.cpu().numpy().view(np.uint64)
+        return [MerkleProof(s) for s in sib]
 
     def poly_device_ptrs(self):
         """Device address of every polynomial's coefficient vector on THIS rank (PolynomialBatch.polynomials, replicated by

@@ -186,6 +186,11 @@ def _gloo_worker(rank, world, port, w, lg_d, r, cap, from_values, q, chunks=1):
         for leaf in leaves:
             pr = b.prove(leaf)
             ok &= bool(oracle.merkle_verify(ref["leaves"][leaf], leaf, ref["cap"], pr.siblings))
+        # the query phase's batched form: one collective for all paths, same siblings as the single-leaf calls
+        many = b.prove_many(leaves)
+        for leaf, pr in zip(leaves, many):
+            ok &= np.array_equal(pr.siblings, b.prove(leaf).siblings)
+            ok &= bool(oracle.merkle_verify(ref["leaves"][leaf], leaf, ref["cap"], pr.siblings))
         if plan.top_levels == 0:
             l0, l1 = plan.leaf_range(rank)
             per = ref["digests"].shape[0] // world
