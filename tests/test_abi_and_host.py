@@ -153,3 +153,27 @@ def test_rust_sys_binding_is_generated_from_header(built_lib):
     assert "polys: *const *const u64" in committed               # const uint64_t* const* polys
     assert "out: *mut *mut pcs_batch" in committed               # pcs_batch** out
     assert "pub fn pcs_last_error() -> *const c_char;" in committed
+
+
+def test_plonk_opening_shape_matches_reference_layout():
+    """PlonkOpeningShape mirrors CommonCircuitData's ranges and get_fri_instance (circuit_data.rs:431-481,586-595) for the
+    m = 64 demo: 4 oracles of 84 / 135 / 20 / 16 polynomials, everything opened at zeta, the 2 Zs also at g * zeta."""
+    from plonky2_demo_b200.fri_prover import PlonkOpeningShape, ext_mul, primitive_root_of_unity
+
+    s = PlonkOpeningShape(degree_bits=15, num_constants=4, num_routed_wires=80, num_wires=135, num_challenges=2,
+                          num_partial_products=9, quotient_degree_factor=8)
+    assert s.oracle_widths() == [84, 135, 20, 16]
+    assert (list(s.constants_range()), s.sigmas_range().start, s.sigmas_range().stop) == ([0, 1, 2, 3], 4, 84)
+    assert list(s.zs_range()) == [0, 1] and (s.partial_products_range().start, s.partial_products_range().stop) == (2, 20)
+    zeta = (11, 22)
+    inst = s.get_fri_instance(zeta)
+    assert [o.num_polys for o in inst.oracles] == [84, 135, 20, 16] and not any(o.blinding for o in inst.oracles)
+    b0, b1 = inst.batches
+    assert b0.point == zeta and len(b0.polynomials) == 255
+    assert [(p.oracle_index, p.polynomial_index) for p in b0.polynomials[:3]] == [(0, 0), (0, 1), (0, 2)]
+    assert (b0.polynomials[84].oracle_index, b0.polynomials[84].polynomial_index) == (1, 0)
+    assert (b0.polynomials[-1].oracle_index, b0.polynomials[-1].polynomial_index) == (3, 15)
+    g = primitive_root_of_unity(15)
+    assert pow(g, 1 << 15, 0xFFFFFFFF00000001) == 1 and pow(g, 1 << 14, 0xFFFFFFFF00000001) != 1
+    assert b1.point == ext_mul((g, 0), zeta)
+    assert [(p.oracle_index, p.polynomial_index) for p in b1.polynomials] == [(2, 0), (2, 1)]
