@@ -67,6 +67,28 @@ __global__ void k_interleave_bitrev(const uint64_t* in, size_t n, unsigned lg_n,
 // ------------------------------------------------------------------------------------------------
 constexpr int EV_THREADS = 256, EV_PER_THREAD = 64, EV_BATCH = 16, EV_CHUNK = EV_THREADS * EV_PER_THREAD;
 
+// Shared tail of the two evaluation kernels: thread t holds S_t = sum_k c[t + 256 k] z^(256 k); the chunk's value is
+// z^(chunk start) * sum_t z^t S_t.
+__device__ __forceinline__ void eval_block_finish(gl::ext2 s, unsigned t, gl::ext2* s_red, const gl::ext2* __restrict__ pw_t,
+                                                  const gl::ext2* __restrict__ pw_c, gl::ext2* __restrict__ partial) {
+    s = gl::ext_canon(gl::ext_mul(s, pw_t[t]));
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {   // warp sum (canonical adds)
+        uint64_t oa = __shfl_down_sync(0xffffffffu, s.a, off), ob = __shfl_down_sync(0xffffffffu, s.b, off);
+        s.a = gl::add(s.a, oa);
+        s.b = gl::add(s.b, ob);
+    }
+    if ((t & 31) == 0) s_red[t >> 5] = s;
+    __syncthreads();
+    if (t == 0) {
+        for (int wp = 1; wp < EV_THREADS / 32; wp++) {
+            s.a = gl::add(s.a, s_red[wp].a);
+            s.b = gl::add(s.b, s_red[wp].b);
+        }
+        partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = gl::ext_canon(gl::ext_mul(s, pw_c[blockIdx.x]));
+    }
+}
+
 // grid (chunks, w).  Thread t of chunk c sums  coeff[c*16384 + t + 256 k] * (z^256)^k  over k < 64 carry-free (ext.cuh
 // lazy6, loads double-buffered in batches of 16), multiplies by z^t; the block adds its 256 partial sums and scales by z^(16384 c).
 __global__ void __launch_bounds__(EV_THREADS) k_eval_ext(const uint64_t* __restrict__ coeffs,
@@ -115,23 +137,7 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_ext(const uint64_t* __restr
         for (int k = 0; k < EV_BATCH; k++) cur[k] = nxt[k];
     }
     gl::ext2 s = {gl::lazy_reduce(A), gl::lazy_reduce(B)};
-    s = gl::ext_canon(gl::ext_mul(s, pw_t[t]));
-    // block sum (canonical adds)
-#pragma unroll
-    for (int off = 16; off; off >>= 1) {
-        uint64_t oa = __shfl_down_sync(0xffffffffu, s.a, off), ob = __shfl_down_sync(0xffffffffu, s.b, off);
-        s.a = gl::add(s.a, oa);
-        s.b = gl::add(s.b, ob);
-    }
-    if ((t & 31) == 0) s_red[t >> 5] = s;
-    __syncthreads();
-    if (t == 0) {
-        for (int wp = 1; wp < EV_THREADS / 32; wp++) {
-            s.a = gl::add(s.a, s_red[wp].a);
-            s.b = gl::add(s.b, s_red[wp].b);
-        }
-        partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = gl::ext_canon(gl::ext_mul(s, pw_c[blockIdx.x]));
-    }
+    eval_block_finish(s, t, s_red, pw_t, pw_c, partial);
 }
 
 // The same sum with the coefficients staged through shared memory by the TMA unit: a block owns 128 KB of ONE polynomial
@@ -203,22 +209,7 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_ext_tma(const uint64_t* __r
         if (t == 0 && g + 2 < n_groups) issue(g + 2);
     }
     gl::ext2 s = {gl::lazy_reduce(A), gl::lazy_reduce(B)};
-    s = gl::ext_canon(gl::ext_mul(s, pw_t[t]));
-#pragma unroll
-    for (int off = 16; off; off >>= 1) {
-        uint64_t oa = __shfl_down_sync(0xffffffffu, s.a, off), ob = __shfl_down_sync(0xffffffffu, s.b, off);
-        s.a = gl::add(s.a, oa);
-        s.b = gl::add(s.b, ob);
-    }
-    if ((t & 31) == 0) s_red[t >> 5] = s;
-    __syncthreads();
-    if (t == 0) {
-        for (int wp = 1; wp < EV_THREADS / 32; wp++) {
-            s.a = gl::add(s.a, s_red[wp].a);
-            s.b = gl::add(s.b, s_red[wp].b);
-        }
-        partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = gl::ext_canon(gl::ext_mul(s, pw_c[blockIdx.x]));
-    }
+    eval_block_finish(s, t, s_red, pw_t, pw_c, partial);
 }
 
 // one block per polynomial: out[j] = sum over chunks
