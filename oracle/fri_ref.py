@@ -19,7 +19,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import P, _arr, _p, hash_or_noop, lib, merkle_build, merkle_prove, merkle_verify, poseidon, reverse_index_bits
+from . import P, _arr, _p, lib, merkle_build, merkle_prove, merkle_verify, poseidon, reverse_index_bits
 
 u64p = C.POINTER(C.c_uint64)
 COSET_SHIFT = 7           # F::MULTIPLICATIVE_GROUP_GENERATOR (goldilocks_field.rs:76)

@@ -15,7 +15,7 @@ from typing import List, Tuple
 import numpy as np
 
 from . import _ffi
-from .fri import FriParams, PolynomialBatch, _DeviceMerkleTree, fri_proof_of_work
+from .fri import PolynomialBatch, _DeviceMerkleTree, fri_proof_of_work
 from .hashing import MerkleCap, MerkleProof, PoseidonPermutation
 from .polynomial import GOLDILOCKS_ORDER, log2_strict
 
