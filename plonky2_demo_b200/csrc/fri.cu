@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(RT_COLS) k_reduce_polys_base_tma(const uint64_
 // ------------------------------------------------------------------------------------------------
 // Suffix scan in segments of SEG coefficients: H_s = segment Horner value, carry_s = the same scan over H with point
 // z^SEG (recursion on the host), then every segment replays its Horner recurrence starting from its carry.
-constexpr int SEG = 64;
+constexpr int SEG = 16;
 
 __global__ void k_seg_horner(const uint64_t* __restrict__ c, size_t c_stride, size_t n, gl::ext2 z, uint64_t* h,
                              size_t h_stride, size_t n_seg) {
