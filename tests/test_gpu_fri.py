@@ -454,3 +454,54 @@ def test_prove_openings_random_instances(pcs):
                                    cap_height, arities, pow_bits, n_q, lg_d), ctx
         for b in gpu:
             b.free()
+
+
+def test_device_pointer_entry_points_alignment_and_errors(pcs):
+    """pcs_eval_ext_dev / pcs_fri_final_poly_dev on scattered polynomials: 16-byte aligned rows take the TMA-staged kernels,
+    rows at an odd multiple of 8 bytes must fall back to the register-staged ones (bulk copies need 16-byte alignment)."""
+    import ctypes as C
+
+    import torch
+
+    from plonky2_demo_b200 import _ffi
+    from plonky2_demo_b200.fri_prover import ExtensionPolynomial, _ext_arg, _poly_ptr_array
+
+    L = _ffi.lib()
+    w, lg_d = 5, 9
+    d = 1 << lg_d
+    c = seeded_polys(w, d, 0xA11C)
+    z, alpha = (0x1234567, 0x7654321), (0xABCDEF, 0x13579B)
+    want_eval = fr.eval_base_polys_ext(c, z)
+    batches = [(z, [(0, j) for j in range(w)]), ((3, 4), [(0, 1), (0, 3)])]
+    want_fin = fr.final_poly([c], batches, alpha)
+    for offset in (0, 1):                                   # in u64 elements: 0 -> aligned, 1 -> base + 8 bytes
+        buf = torch.zeros(w * (d + 2) + 2, dtype=torch.int64, device="cuda")
+        addrs = []
+        for j in range(w):
+            start = j * (d + 2) + offset                    # rows 2 elements apart keep every row at the same parity
+            buf[start:start + d] = torch.from_numpy(c[j].view(np.int64)).cuda()
+            addrs.append(buf.data_ptr() + 8 * start)
+        assert all((a % 16 == 0) == (offset == 0) for a in addrs)
+        torch.cuda.synchronize()
+        out = np.empty((w, 2), dtype=np.uint64)
+        _ffi.check(L.pcs_eval_ext_dev(_poly_ptr_array(addrs), w, lg_d, _ext_arg(z), _ffi.ptr(out)))
+        assert np.array_equal(out, want_eval), offset
+        order = [addrs[j] for _, polys in batches for _, j in polys]
+        pts = np.array([[pt[0], pt[1]] for pt, _ in batches], dtype=np.uint64)
+        lens = (C.c_size_t * 2)(w, 2)
+        h = C.c_void_p()
+        _ffi.check(L.pcs_fri_final_poly_dev(_poly_ptr_array(order), lg_d, 2, _ffi.ptr(pts), lens, _ext_arg(alpha), C.byref(h)))
+        p = ExtensionPolynomial(h)
+        assert np.array_equal(p.coeffs, want_fin), offset
+        p.free()
+    # errors
+    out = np.empty((w, 2), dtype=np.uint64)
+    bad = _poly_ptr_array(addrs)
+    bad[2] = None
+    with pytest.raises(pcs.PcsError, match="NULL polynomial"):
+        _ffi.check(L.pcs_eval_ext_dev(bad, w, lg_d, _ext_arg(z), _ffi.ptr(out)))
+    h = C.c_void_p()
+    with pytest.raises(pcs.PcsError, match="empty FRI batch"):
+        _ffi.check(L.pcs_fri_final_poly_dev(_poly_ptr_array(order), lg_d, 2, _ffi.ptr(pts), (C.c_size_t * 2)(w, 0), _ext_arg(alpha), C.byref(h)))
+    with pytest.raises(pcs.PcsError, match="TWO_ADICITY"):
+        _ffi.check(L.pcs_eval_ext_dev(_poly_ptr_array(addrs), w, 33, _ext_arg(z), _ffi.ptr(out)))
