@@ -471,6 +471,17 @@ def run_ours(a):
     int_pipe = {"permutations_per_s": (n_perm_leaf) / (leaf_ms * 1e-3),
                 "clk_per_permutation_per_sm_lane": (leaf_ms * 1e-3) * sm_mhz * 1e6 * 148 / max(n_perm_leaf, 1),
                 "sm_mhz_used": sm_mhz}
+    # issue-slot view of the same launch: instructions per permutation are a property of the compiled kernel (ncu
+    # smsp__inst_executed x 32 / permutations, profiles/r01_poseidon_v3.md); an SM issues 4 x 32 thread-instructions per clock
+    INSTR_PER_PERMUTATION = 16950.0
+    issue_peak = 148 * 128 * sm_mhz * 1e6
+    int_pipe.update({
+        "thread_instr_per_permutation": INSTR_PER_PERMUTATION,
+        "thread_instr_per_s": INSTR_PER_PERMUTATION * int_pipe["permutations_per_s"],
+        "issue_peak_thread_instr_per_s": issue_peak,
+        "issue_frac": INSTR_PER_PERMUTATION * int_pipe["permutations_per_s"] / issue_peak,
+        "note": "the kernel's real ceiling: 64-bit modular arithmetic on 32-bit integer / FP64 pipes; measured pipe shares in "
+                "profiles/r01_poseidon_v3.md (FMA-heavy 51 % + FP64 47 % on one shared issue pipe, ALU 47 %)"})
     kernels = {
         "lde_standalone": None if lde_alone is None else {
             "workload": f"standalone batched coset LDE: {w} polys x 2^{lg_d}, rate_bits {r} (pcs_coset_lde_dev, 2 launches)",
