@@ -505,3 +505,36 @@ def test_device_pointer_entry_points_alignment_and_errors(pcs):
         _ffi.check(L.pcs_fri_final_poly_dev(_poly_ptr_array(order), lg_d, 2, _ffi.ptr(pts), (C.c_size_t * 2)(w, 0), _ext_arg(alpha), C.byref(h)))
     with pytest.raises(pcs.PcsError, match="TWO_ADICITY"):
         _ffi.check(L.pcs_eval_ext_dev(_poly_ptr_array(addrs), w, 33, _ext_arg(z), _ffi.ptr(out)))
+
+
+def test_full_size_opening_properties(pcs):
+    """BASELINE's headline shape (135 x 2^20, rate 3): the oracle cannot redo the whole opening proof in seconds, so the
+    device results are checked through size-independent identities -- sampled polynomials against the CPU Horner
+    evaluation, and the quotient identity  final(x) * (x - z) == F(x) - F(z)  with F = sum_j alpha^j f_j, at a random x,
+    where F(x), F(z) come from device openings and final(x) from a CPU evaluation of the device's final polynomial."""
+    from plonky2_demo_b200.fri_prover import FriBatchInfo, FriInstanceInfo, FriOracleInfo, FriPolynomialInfo, eval_commitment, final_poly
+
+    w, lg_d = 135, 20
+    rng = np.random.default_rng(2026)
+    coeffs = rng.integers(0, 1 << 64, size=(w, 1 << lg_d), dtype=np.uint64)        # any u64: non-canonical inputs included
+    b = pcs.PolynomialBatch.from_coeffs(coeffs, 3, False, 4, keep_coeffs=True)
+    prng = random.Random(7)
+    z, x, alpha = rand_ext(prng), rand_ext(prng), rand_ext(prng)
+    at_z, at_x = eval_commitment(z, b), eval_commitment(x, b)
+    for j in (0, 67, 134):
+        assert tuple(int(v) for v in at_z[j]) == tuple(int(v) for v in fr.eval_base_polys_ext(coeffs[j:j + 1], z)[0])
+    inst = FriInstanceInfo([FriOracleInfo(w, False)], [FriBatchInfo(z, FriPolynomialInfo.from_range(0, range(w)))])
+    fin = final_poly(inst, [b], alpha)
+    fc = fin.coeffs
+    assert fc.shape == (1 << lg_d, 2) and (int(fc[-1, 0]), int(fc[-1, 1])) == (0, 0)   # quotient padded with one zero
+
+    def combine(vals):
+        acc = (0, 0)
+        for v in reversed(vals):
+            acc = fr.ext_add(fr.ext_mul(acc, alpha), (int(v[0]), int(v[1])))
+        return acc
+
+    lhs = fr.ext_mul(fr.ext_poly_eval(fc, x), fr.ext_sub(x, z))
+    assert lhs == fr.ext_sub(combine(at_x), combine(at_z))
+    fin.free()
+    b.free()
