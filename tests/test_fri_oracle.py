@@ -277,3 +277,64 @@ def test_fri_prover_verifier_roundtrip(lg_d, rate_bits, cap_height, arities, wid
         st[1, 1] = (int(st[1, 1]) + 1) % P
         with pytest.raises(AssertionError):
             fr.verify_fri_proof(batches, openings, ch.clone(), caps, bad, *args)
+
+
+def test_fri_roundtrip_random_shapes_and_more_tampering():
+    """Ten seeded random shapes through the restated prover and verifier, then the tamper classes the parametrised test does
+    not cover: proof-of-work witness, a commit-phase cap, a Merkle path, a proof transplanted onto another transcript."""
+    import copy
+
+    rng = random.Random(424242)
+    for case in range(10):
+        lg_d = rng.randrange(1, 8)
+        rate_bits = rng.randrange(1, 4)
+        widths = [rng.randrange(1, 6) for _ in range(rng.randrange(1, 4))]
+        arities, left = [], lg_d
+        while left > 0 and rng.random() < 0.7:
+            a = rng.randrange(1, min(3, left) + 1)
+            arities.append(a)
+            left -= a
+        min_leaves_log = min([lg_d + rate_bits] + [lg_d + rate_bits - sum(arities[: i + 1]) for i in range(len(arities))])
+        cap_height = rng.randrange(0, min(min_leaves_log, 3) + 1)
+        pow_bits, n_q = rng.randrange(0, 7), rng.randrange(1, 5)
+        oracles, batches = make_instance(lg_d, rate_bits, cap_height, widths, seed=case)
+        openings = openings_of(oracles, batches)
+        ch = seeded_challenger(oracles, openings)
+        proof = fr.prove_openings(oracles, batches, ch.clone(), rate_bits, cap_height, arities, pow_bits, n_q)
+        caps = [o["cap"] for o in oracles]
+        args = (rate_bits, cap_height, arities, pow_bits, n_q, lg_d)
+        assert fr.verify_fri_proof(batches, openings, ch.clone(), caps, proof, *args), (case, lg_d, rate_bits, arities)
+        if case % 3 == 0:
+            # a different transcript (one more observed element) must not accept the same proof
+            other = ch.clone()
+            other.observe_element(1)
+            with pytest.raises(AssertionError):
+                fr.verify_fri_proof(batches, openings, other, caps, proof, *args)
+            # wrong initial cap
+            bad_caps = [c.copy() for c in caps]
+            bad_caps[0][0, 0] = (int(bad_caps[0][0, 0]) + 1) % P
+            with pytest.raises(AssertionError):
+                fr.verify_fri_proof(batches, openings, ch.clone(), bad_caps, proof, *args)
+            if cap_height < lg_d + rate_bits:
+                bad = copy.deepcopy(proof)
+                path = bad["query_round_proofs"][0]["initial_trees_proof"][0][1]
+                path[0, 0] = (int(path[0, 0]) + 1) % P
+                with pytest.raises(AssertionError):
+                    fr.verify_fri_proof(batches, openings, ch.clone(), caps, bad, *args)
+            if arities:
+                bad = copy.deepcopy(proof)
+                bad["commit_phase_merkle_caps"][0] = bad["commit_phase_merkle_caps"][0].copy()
+                bad["commit_phase_merkle_caps"][0][0, 1] = (int(bad["commit_phase_merkle_caps"][0][0, 1]) + 1) % P
+                with pytest.raises(AssertionError):
+                    fr.verify_fri_proof(batches, openings, ch.clone(), caps, bad, *args)
+    # proof of work: with 12 bits a random witness almost surely fails
+    oracles, batches = make_instance(5, 2, 1, [3, 2], seed=99)
+    openings = openings_of(oracles, batches)
+    ch = seeded_challenger(oracles, openings)
+    proof = fr.prove_openings(oracles, batches, ch.clone(), 2, 1, [2], 12, 3)
+    args = (2, 1, [2], 12, 3, 5)
+    assert fr.verify_fri_proof(batches, openings, ch.clone(), [o["cap"] for o in oracles], proof, *args)
+    bad = dict(proof)
+    bad["pow_witness"] = proof["pow_witness"] + 1
+    with pytest.raises(AssertionError):
+        fr.verify_fri_proof(batches, openings, ch.clone(), [o["cap"] for o in oracles], bad, *args)
