@@ -402,3 +402,156 @@ def test_cuda_opening_proof_over_sharded_oracles(chunks):
         b.free()
     for f in (f1, f2, mixed):
         f.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# opening proof over a commitment sharded across two gloo ranks (CPU): the product's host glue (prove_openings, fri_proof,
+# fri_committed_trees, the batched query phase) and the collectives of ShardedPolynomialBatch run for real; the device entry
+# points they call are replaced by oracle-backed stand-ins, as OracleShardEngine does for the commit.
+# ---------------------------------------------------------------------------------------------
+def _gloo_opening_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    from oracle import fri_ref as fr
+    from plonky2_demo_b200 import fri_prover as fp
+    from plonky2_demo_b200.fri import FriConfig, FriReductionStrategy
+    from plonky2_demo_b200.hashing import MerkleCap, MerkleProof, PoseidonPermutation
+    from plonky2_demo_b200.sharded import ShardedPolynomialBatch, ShardPlan
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lg_d, r, cap, widths, arities, pow_bits, n_q = 6, 2, 2, [5, 3], [2, 2], 4, 5
+        coeffs = [seeded_polys(w, 1 << lg_d, base_seed=900 + k) for k, w in enumerate(widths)]
+
+        # ---- stand-ins for the device entry points ----
+        PoseidonPermutation.permute = lambda self: setattr(self, "state", oracle.poseidon(self.state)[0])
+
+        class _Tree:
+            def __init__(self, leaves, cap_height):
+                self.leaves, self.cap_height = leaves, cap_height
+                self.digests, cap_ = oracle.merkle_build(leaves, cap_height)
+                self.merkle_tree = type("T", (), {"cap": MerkleCap(cap_)})()
+
+            def get_rows(self, idx):
+                return self.leaves[np.asarray(list(idx), dtype=np.int64)]
+
+            def prove_many(self, idx):
+                return [MerkleProof(oracle.merkle_prove(self.digests, self.leaves.shape[0], self.cap_height, int(i))) for i in idx]
+
+            def free(self):
+                pass
+
+        class _ExtPoly:
+            def __init__(self, c):
+                self.c = c
+
+            def __len__(self):
+                return self.c.shape[0]
+
+            @property
+            def coeffs(self):
+                return self.c
+
+            def commit_layer(self, rate_bits, shift, arity_bits, cap_height):
+                vals = fr.ext_coset_lde(self.c, rate_bits, shift)
+                n = vals.shape[0]
+                idx = oracle.reverse_index_bits(np.arange(n, dtype=np.uint64)).astype(np.int64)
+                return _Tree(np.ascontiguousarray(vals[idx].reshape(n >> arity_bits, 2 << arity_bits)), cap_height)
+
+            def fold(self, arity_bits, beta):
+                self.c = fr.fri_fold(self.c, 1 << arity_bits, beta)
+
+            def free(self):
+                pass
+
+        def _final_poly(instance, oracles, alpha):
+            full = [o._coeffs.numpy().view(np.uint64)[: o.n_polys] for o in oracles]      # replicated by the exchange
+            batches = [(b.point, [(p.oracle_index, p.polynomial_index) for p in b.polynomials]) for b in instance.batches]
+            return _ExtPoly(fr.final_poly(full, batches, alpha))
+
+        def _pow(state, buf, cfg):
+            ch = fr.Challenger()
+            ch.sponge_state, ch.input_buffer = [int(x) for x in state], [int(x) for x in buf]
+            return fr.fri_proof_of_work(ch, cfg.proof_of_work_bits)
+
+        fp.final_poly, fp.fri_proof_of_work = _final_poly, _pow
+
+        # ---- the sharded commitments (oracle-backed shard engine, real gloo collectives) ----
+        eng = OracleShardEngine()
+        sharded = []
+        for c in coeffs:
+            plan = ShardPlan(c.shape[0], lg_d, r, cap, world, 1)
+            local = torch.from_numpy(np.ascontiguousarray(c[plan.local_polys(rank)]).view(np.int64).copy())
+            sharded.append(ShardedPolynomialBatch.from_coeffs(local, c.shape[0], r, cap, engine=eng))
+        zeta = (123456789, 987654321)
+        zeta_next = fr.ext_mul((fr.primitive_root_of_unity(lg_d), 0), zeta)
+        batches = [(zeta, [(k, j) for k, w in enumerate(widths) for j in range(w)]), (zeta_next, [(1, 0), (1, 2)])]
+        inst = fp.FriInstanceInfo([fp.FriOracleInfo(w, False) for w in widths],
+                                  [fp.FriBatchInfo(pt, [fp.FriPolynomialInfo(o, j) for o, j in polys]) for pt, polys in batches])
+        openings = [[tuple(int(x) for x in fr.eval_base_polys_ext(coeffs[o][j:j + 1], pt)[0]) for o, j in polys]
+                    for pt, polys in batches]
+        params = FriConfig(r, cap, pow_bits, FriReductionStrategy.Fixed(arities), n_q).fri_params(lg_d, False)
+
+        def transcript(cls):
+            ch = cls()
+            for b in sharded:
+                ch.observe_cap(b.cap)
+            for vals in openings:
+                ch.observe_extension_elements(vals)
+            return ch
+
+        proof = fp.prove_openings(inst, sharded, transcript(fp.Challenger), params)      # collective
+        # reference: the restated prover over the unsharded commitments
+        cpu = []
+        for c in coeffs:
+            o = oracle.commit_from_coeffs(c, r, cap)
+            o["coeffs"], o["cap_height"] = c, cap
+            cpu.append(o)
+        want = fr.prove_openings(cpu, batches, transcript(fr.Challenger), r, cap, arities, pow_bits, n_q)
+        ok = all(np.array_equal(b.cap, o["cap"]) for b, o in zip(sharded, cpu))
+        ok &= proof.pow_witness == want["pow_witness"] and proof.fri_query_indices == want["_indices"]
+        ok &= bool(np.array_equal(proof.final_poly, want["final_poly"]))
+        ok &= all(np.array_equal(c.hashes, wc) for c, wc in zip(proof.commit_phase_merkle_caps, want["commit_phase_merkle_caps"]))
+        for rr, wr in zip(proof.query_round_proofs, want["query_round_proofs"]):
+            for (ev, mp), (wev, wmp) in zip(rr.initial_trees_proof.evals_proofs, wr["initial_trees_proof"]):
+                ok &= bool(np.array_equal(ev, wev)) and bool(np.array_equal(np.asarray(mp.siblings).reshape(-1, 4), wmp))
+            for s, ws in zip(rr.steps, wr["steps"]):
+                ok &= bool(np.array_equal(s.evals, ws["evals"]))
+                ok &= bool(np.array_equal(np.asarray(s.merkle_proof.siblings).reshape(-1, 4), ws["merkle_proof"]))
+        as_oracle = {
+            "commit_phase_merkle_caps": [c.hashes for c in proof.commit_phase_merkle_caps], "final_poly": proof.final_poly,
+            "pow_witness": proof.pow_witness,
+            "query_round_proofs": [
+                {"initial_trees_proof": [(ev, np.asarray(mp.siblings).reshape(-1, 4)) for ev, mp in rr.initial_trees_proof.evals_proofs],
+                 "steps": [{"evals": s.evals, "merkle_proof": np.asarray(s.merkle_proof.siblings).reshape(-1, 4)} for s in rr.steps]}
+                for rr in proof.query_round_proofs]}
+        ok &= bool(fr.verify_fri_proof(batches, openings, transcript(fr.Challenger), [o["cap"] for o in cpu], as_oracle, r, cap,
+                                       arities, pow_bits, n_q, lg_d))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_opening_proof_over_sharded_commitments():
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_opening_worker, args=(k, 2, port, q)) for k in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
