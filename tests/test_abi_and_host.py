@@ -177,3 +177,22 @@ def test_plonk_opening_shape_matches_reference_layout():
     assert pow(g, 1 << 15, 0xFFFFFFFF00000001) == 1 and pow(g, 1 << 14, 0xFFFFFFFF00000001) != 1
     assert b1.point == ext_mul((g, 0), zeta)
     assert [(p.oracle_index, p.polynomial_index) for p in b1.polynomials] == [(2, 0), (2, 1)]
+
+
+def test_streaming_kernels_use_tma_bulk_copies(built_lib):
+    """The HBM-facing opening-proof kernels stage their input with the TMA unit: the compiled object must contain the bulk
+    copy (UBLKCP) and mbarrier (SYNCS) SASS (B200_PROFILING.md: the mnemonics that prove TMA), for sm_100a."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    obj = os.path.join(ROOT, "plonky2_demo_b200", "build", "fri.o")
+    if not os.path.exists(cuobjdump) or not os.path.exists(obj):
+        pytest.skip("cuobjdump or the object file is not available")
+    sass = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for kernel in ("k_eval_ext_tma", "k_reduce_polys_base_tma"):
+        body = sass[sass.index(kernel):]
+        body = body[: body.index("Function :", 10)] if "Function :" in body[10:] else body
+        assert "UBLKCP" in body, kernel
+        assert "SYNCS" in body, kernel
