@@ -34,6 +34,9 @@
 #include <vector>
 
 #include "common.cuh"
+#ifndef PCS_REDUCE_MAD
+#define PCS_REDUCE_MAD 1   // NTT only: the butterfly is ALU-pipe bound, the multiply-add reduction trades 3 ALU ops for one IMAD.HI
+#endif
 #include "gl64.cuh"
 
 namespace pcs {
