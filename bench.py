@@ -39,10 +39,22 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 METRIC = "lde_merkle_commit_elems_per_s"
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_hash_cols launch from an `ncu --set full` capture of this
-# very command, keyed by (width, lg_d, rate_bits, n_gpus); None where no capture exists.
-NCU_TRAFFIC = {(135, 20, 3, 1): 9082833000 + 273173248}
-NCU_TRAFFIC_SOURCE = "profiles/r01_leafhash_v5.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_hash_cols launch, from the `ncu --set full` capture of this very
+# command on the shipped build (tools/gpu_profile.sh writes profiles/leafhash_traffic.json next to the summary it comes from)
+def ncu_traffic(width, lg_d, rate_bits, n_gpus):
+    p = os.path.join(ROOT, "profiles", "leafhash_traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)
+    except (OSError, ValueError):
+        return None, "no capture"
+    key = f"{width}x2^{lg_d}_r{rate_bits}_g{n_gpus}"
+    e = t.get(key)
+    if not e:
+        return None, "no capture for this shape"
+    return int(e["dram_bytes_read"]) + int(e["dram_bytes_write"]), e.get("source", "profiles/leafhash_traffic.json")
+
+
 UNIT = "elems/s"
 
 
@@ -58,6 +70,12 @@ def parse():
     ap.add_argument("--cap-height", type=int, default=4)
     ap.add_argument("--cpu-sample-lg-d", type=int, default=16, help="degree_log of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-full-size", default="auto", choices=["auto", "on", "off"],
+                    help="--impl reference: also run the full 2^lg_d configuration on the CPU (auto: when it fits the budgets)")
+    ap.add_argument("--reference-budget-s", type=float, default=150.0)
+    ap.add_argument("--large-commit", default="auto", choices=["auto", "on", "off"],
+                    help="N = 8: add BASELINE configs[4], one 135 x 2^24 commitment sharded over the box, with sampled-leaf parity")
+    ap.add_argument("--no-from-values", action="store_true", help="skip the from_values timing at the headline size")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fri", action="store_true", help="skip the opening-proof (FRI) timings")
     ap.add_argument("--chunks", type=int, default=2,
@@ -74,6 +92,11 @@ def workload_name(a):
     return f"PolynomialBatch::from_coeffs commit: {a.width} polys x 2^{a.lg_d}, rate_bits {a.rate_bits}, Poseidon MerkleTree cap_height {a.cap_height}"
 
 
+def bench_config(a):
+    """`config` of the JSON line: identical for both arms (the driver compares them)."""
+    return {"workload": workload_name(a), "elems_per_step": a.width * (1 << (a.lg_d + a.rate_bits))}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -85,7 +108,7 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (port of the reference's CPU path) on a bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_commit_once(width, lg_d, rate_bits, cap_height):
+def cpu_commit_once(width, lg_d, rate_bits, cap_height, keep=False):
     import oracle
     from helpers import seeded_polys
 
@@ -93,51 +116,89 @@ def cpu_commit_once(width, lg_d, rate_bits, cap_height):
     t0 = time.perf_counter()
     out = oracle.commit_from_coeffs(coeffs, rate_bits, cap_height)
     dt = time.perf_counter() - t0
-    return dt, out["cap"]
+    cap = out["cap"].copy()
+    del out
+    return dt, cap
+
+
+def _mem_available_bytes():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 0
 
 
 def cpu_baseline(a):
     import oracle
 
+    cores = oracle.use_all_cores()   # torchrun exports OMP_NUM_THREADS=1: the reference's rayon pool uses every core
     lg = min(a.cpu_sample_lg_d, a.lg_d)
     dt, _ = cpu_commit_once(a.width, lg, a.rate_bits, a.cap_height)
     elems = a.width * (1 << (lg + a.rate_bits))
     return {
         "value": elems / dt,
         "unit": UNIT,
-        "cores": oracle.num_threads(),
+        "cores": cores,
         "kind": "port",
         "sample": f"one from_coeffs commit of {a.width} x 2^{lg} (rate_bits {a.rate_bits}, cap_height {a.cap_height}), "
-                  f"{dt:.2f} s wall on {oracle.num_threads()} OpenMP threads; C port of the reference CPU algorithm (oracle/oracle.c)",
+                  f"{dt:.2f} s wall on {cores} OpenMP threads; C port of the reference CPU algorithm (oracle/oracle.c)",
     }
 
 
 def run_reference(a):
-    """--impl reference: CPU port of the reference path, all host threads, bounded sample per step."""
+    """--impl reference: the CPU port of the reference path on ALL host cores (whatever OMP_NUM_THREADS torchrun exported).
+    K bounded-sample steps (135 x 2^cpu_sample_lg_d), then -- when it fits the time and memory budget -- the FULL
+    configuration itself (one run; every step when K <= 3), which then is the reported value.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
 
+    cores = oracle.use_all_cores()
     lg = min(a.cpu_sample_lg_d, a.lg_d)
-    for _ in range(a.warmup):
+    for _ in range(min(a.warmup, 2)):
         cpu_commit_once(a.width, lg, a.rate_bits, a.cap_height)
     times = []
     for _ in range(a.steps):
         dt, _ = cpu_commit_once(a.width, lg, a.rate_bits, a.cap_height)
         times.append(dt)
     total = sum(times)
-    elems = a.width * (1 << (lg + a.rate_bits))
-    value = elems * a.steps / total
-    sample = (f"each step = one from_coeffs commit of {a.width} x 2^{lg} (rate_bits {a.rate_bits}, cap_height {a.cap_height}); "
-              f"bounded sample of the 2^{a.lg_d} workload; elems/s is size-normalised")
+    elems_s = a.width * (1 << (lg + a.rate_bits))
+    sample_value = elems_s * a.steps / total
+    sample = (f"{a.steps} steps, each one from_coeffs commit of {a.width} x 2^{lg} (rate_bits {a.rate_bits}, cap_height {a.cap_height}) "
+              f"= a bounded sample of the 2^{a.lg_d} workload, elems/s size-normalised; {cores} OpenMP threads")
+    value, ms_per_step, same = sample_value, 1e3 * total / a.steps, lg == a.lg_d
+    full = None
+    elems_f = a.width * (1 << (a.lg_d + a.rate_bits))
+    if lg < a.lg_d and a.reference_full_size != "off":
+        predicted = (total / a.steps) * (1 << (a.lg_d - lg)) * 1.4        # cache effects make the big case slower per element
+        n_full = a.steps if a.steps <= 3 else 1
+        need = int(elems_f * 8 * 2.6)                                      # LDE + transposed leaves + coefficients + digests
+        avail = _mem_available_bytes()
+        if a.reference_full_size == "on" or (predicted * n_full <= a.reference_budget_s and avail >= need):
+            ft = []
+            for _ in range(n_full):
+                dt, _ = cpu_commit_once(a.width, a.lg_d, a.rate_bits, a.cap_height)
+                ft.append(dt)
+            full = {"runs": n_full, "s_per_commit": ft, "value": elems_f * n_full / sum(ft), "unit": UNIT}
+            value, ms_per_step, same = full["value"], 1e3 * sum(ft) / n_full, True
+            sample = (f"the full configuration: {n_full} from_coeffs commit(s) of {a.width} x 2^{a.lg_d} ({sum(ft) / n_full:.1f} s each) on "
+                      f"{cores} OpenMP threads, after {a.steps} sample steps at 2^{lg} ({sample_value:.3e} elems/s)")
+        else:
+            full = {"skipped": f"predicted {predicted * n_full:.0f} s (budget {a.reference_budget_s} s), needs {need >> 30} GiB of host memory "
+                               f"({avail >> 30} GiB available)"}
     print(json.dumps({
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64 (Goldilocks field, integer)", "data": "synthetic",
-        "config": {"workload": workload_name(a), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample},
+        "config": bench_config(a),
+        "measured_on_full_config": same, "sample_value": sample_value, "full_size": full,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -274,6 +335,72 @@ def fri_opening_bench(pcs, w, lg_d, r, cap_h, dev_ptrs, steps, peak_gbs):
     }
     b.free()
     return out
+
+
+def large_commit_bench(a, world, rank, dev, stream, lg_d=24):
+    """BASELINE.json configs[4]: 135 polys x 2^24, rate_bits 3 (2^27 leaves, 145 GB of LDE rows) sharded over the box.
+    The rows never leave the GPUs; parity at this size is sampled: leaves fetched with their Merkle paths,
+    (i) every path verified against the gathered cap by the CPU oracle, (ii) rows compared with a direct CPU evaluation
+    of the polynomials at the leaf's domain point g * w_N^brev(leaf) (fri/verifier.rs:185-186 pins this order)."""
+    import torch
+    import torch.distributed as dist
+
+    import oracle
+    from helpers import P, brev, splitmix64_stream
+    from plonky2_demo_b200.sharded import ShardedPolynomialBatch, ShardPlan
+
+    w, r, cap_h = a.width, a.rate_bits, a.cap_height
+    d = 1 << lg_d
+    plan = ShardPlan(w, lg_d, r, cap_h, world, a.chunks)
+    mine = plan.local_polys(rank)
+    t0 = time.perf_counter()
+    host = np.empty((len(mine), d), dtype=np.uint64)
+    for j, pj in enumerate(mine):
+        host[j] = splitmix64_stream(0x5EED0000 + pj, d)
+    local = torch.from_numpy(host.view(np.int64)).to(dev)
+    gen_s = time.perf_counter() - t0
+    times, batch = [], None
+    for _ in range(3):
+        if batch is not None:
+            batch.free()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        batch = ShardedPolynomialBatch.from_coeffs(local, w, r, cap_h, partitioned=True, exchange=a.exchange, chunks=plan.chunks)
+        e1.record(stream)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+    n = plan.n_leaves
+    rng = np.random.default_rng(7)
+    leaves = sorted(set([0, n - 1] + [int(x) for x in rng.integers(0, n, size=3)]))
+    rows = batch.get_rows(leaves)
+    paths = batch.prove_many(leaves)
+    ok_paths = True
+    if rank == 0:
+        for k, leaf in enumerate(leaves):
+            ok_paths &= bool(oracle.merkle_verify(rows[k], leaf, batch.cap, paths[k].siblings))
+    lg_n = lg_d + r
+    wN = oracle.primitive_root_of_unity(lg_n)
+    ok_rows, n_eval = True, min(2, len(mine))
+    for k, leaf in enumerate(leaves):
+        x = 7 * pow(wN, brev(leaf, lg_n), P) % P
+        for j in range(n_eval):
+            ok_rows &= int(rows[k][mine[j]]) == oracle.poly_eval(host[j], x)
+    flag = torch.tensor([int(ok_rows)], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res = {"workload": f"large commit: {w} polys x 2^{lg_d}, rate_bits {r}, cap_height {cap_h}, sharded over {world} GPUs",
+           "ms": times, "best_ms": min(times), "elems_per_s": w * n / (min(times) * 1e-3), "lde_bytes": w * n * 8,
+           "exchange": batch.exchange, "sampled_leaves": leaves, "merkle_paths_verify_against_cap": bool(ok_paths),
+           "rows_equal_direct_cpu_evaluation": bool(flag.item()), "polys_evaluated_per_rank": n_eval,
+           "input_generation_s": gen_s}
+    batch.free()
+    del local, host
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_ours(a):
@@ -430,6 +557,30 @@ def run_ours(a):
         lde_alone = g0.elapsed_time(g1) / a.steps
         del lde_out
 
+    # ---- PolynomialBatch::from_values at the same size (oracle.rs:43-65: IFFT of every column first), device resident ----
+    from_values = None
+    if world == 1 and not a.no_from_values:
+        def commit_values():
+            h = C.c_void_p()
+            _ffi.check(L.pcs_commit_from_values(dev_ptrs, w, lg_d, r, cap_h, None, 0, _ffi.PCS_DEVICE_PTRS, None, None, C.byref(h)))
+            return h
+        for _ in range(2):
+            free(commit_values())
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        _ffi.check(L.pcs_timing_totals(None, None, 1))
+        v0.record(stream)
+        for _ in range(a.steps):
+            free(commit_values())
+        v1.record(stream)
+        torch.cuda.synchronize()
+        fv_ms = v0.elapsed_time(v1) / a.steps
+        fv5 = (C.c_float * 5)()
+        _ffi.check(L.pcs_timing_totals(fv5, None, 1))
+        from_values = {"workload": workload_name(a).replace("from_coeffs", "from_values"), "ms": fv_ms,
+                       "elems_per_s": elems / (fv_ms * 1e-3), "ifft_ms": float(fv5[0]) / a.steps,
+                       "note": "the seeded arrays taken as point VALUES; IFFT (size-d inverse NTT of every column) + the from_coeffs path"}
+
     # ---- the opening proof over the committed batch (single GPU) ----
     fri = None
     if world == 1 and not a.no_fri:
@@ -479,7 +630,7 @@ def run_ours(a):
     roofline = {"bound": "hbm", "kernel": "k_hash_cols (Poseidon leaf hashing, 17 permutations per 135-element leaf)",
                 "achieved": leaf_bytes / (leaf_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": leaf_bytes / (leaf_ms * 1e-3) / 1e9 / peak,
-                "traffic": NCU_TRAFFIC.get((w, lg_d, r, world)), "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src,
+                "traffic": ncu_traffic(w, lg_d, r, world)[0], "traffic_source": ncu_traffic(w, lg_d, r, world)[1], "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": leaf_bytes, "launch_ms": leaf_ms,
                 "note": "integer-pipe bound, not HBM bound: see int_pipe"}
     sm_mhz = clocks.get("sm_mhz") or 1965.0
@@ -520,26 +671,73 @@ def run_ours(a):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64 (Goldilocks field, integer)", "data": "synthetic",
-        "config": {"workload": workload_name(a), "elems_per_step": elems, "input_coeff_elems_per_s": value / (1 << r),
-                   "l2_policy": "inputs larger than L2 (1.13 GB coefficients, 9.06 GB LDE per step)",
-                   "parallelism": (f"one commitment sharded over {world} GPUs by coset block (contiguous leaf ranges); coefficient exchange = "
-                                   f"{prev_exchange}; per-rank LDE + hashing; NCCL all-gather of the cap") if world > 1 else "single GPU"},
+        "config": dict(bench_config(a), l2_policy="inputs larger than L2 (1.13 GB coefficients, 9.06 GB LDE per step); no flush needed",
+                       parallelism=(f"one commitment sharded over {world} GPUs by coset block (contiguous leaf ranges); coefficient exchange = "
+                                    f"{prev_exchange}; per-rank LDE + hashing; NCCL all-gather of the cap") if world > 1 else "single GPU"),
+        "input_coeff_elems_per_s": value / (1 << r),
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
         "roofline": roofline, "int_pipe": int_pipe, "kernels": kernels,
         "phase_ms": {"IFFT": phase[0], "FFT + blinding": phase[1], "transpose LDEs": phase[2], "leaf hashing": phase[3], "node levels": phase[4]},
     }
+    out["kernels"]["from_values"] = from_values
+
+    # ---- parity of what was just timed (every N): the benchmark checks itself against the oracle and the 1-GPU engine ----
+    import oracle
+    from helpers import seeded_polys as sp
+    parity = {}
+    lg_s = min(a.cpu_sample_lg_d, lg_d)
+    if world == 1:
+        small = sp(w, 1 << lg_s, base_seed=0x5EED0000)
+        if rank == 0:
+            ref_small = oracle.commit_from_coeffs(small, r, cap_h)
+            b = pcs.PolynomialBatch.from_coeffs(small, r, False, cap_h)
+            parity["cap_equal_to_oracle_at_sample_size"] = bool(np.array_equal(b.merkle_tree.cap.hashes, ref_small["cap"]))
+            b.free()
+            b = pcs.PolynomialBatch.from_values(oracle.fft(small), r, False, cap_h)
+            parity["from_values_cap_equal_to_oracle_at_sample_size"] = bool(np.array_equal(b.merkle_tree.cap.hashes, ref_small["cap"]))
+            b.free()
+    else:
+        # (i) the SHARDED path (real NCCL exchange, streaming chunks) against the CPU oracle at the sample size
+        plan_s = ShardPlan(w, lg_s, r, cap_h, world, plan.chunks)
+        mine_s = plan_s.local_polys(rank)
+        loc = np.stack([splitmix64_stream(0x5EED0000 + pj, 1 << lg_s) for pj in mine_s]) if mine_s else np.empty((0, 1 << lg_s), np.uint64)
+        bs = ShardedPolynomialBatch.from_coeffs(torch.from_numpy(loc.view(np.int64)).to(dev), w, r, cap_h, partitioned=True,
+                                                exchange=a.exchange, chunks=plan_s.chunks)
+        cap_s = np.array(bs.cap)
+        leaf_s = (1 << (lg_s + r)) - 5
+        row_s = bs.get_rows([leaf_s])[0]
+        path_s = bs.prove(leaf_s)
+        bs.free()
+        if rank == 0:
+            ref_small = oracle.commit_from_coeffs(sp(w, 1 << lg_s, base_seed=0x5EED0000), r, cap_h)
+            parity["sharded_cap_equal_to_oracle_at_sample_size"] = bool(np.array_equal(cap_s, ref_small["cap"]))
+            parity["sharded_row_equal_to_oracle"] = bool(np.array_equal(row_s, ref_small["leaves"][leaf_s]))
+            parity["sharded_path_verifies_against_cap"] = bool(oracle.merkle_verify(row_s, leaf_s, cap_s, path_s.siblings))
+        # (ii) the timed commitment itself against the SAME commitment on one GPU (the unsharded engine on rank 0)
+        if rank == 0:
+            full = torch.empty((w, d), dtype=torch.int64, pin_memory=True)
+            fn = full.numpy().view(np.uint64)
+            for j in range(w):
+                fn[j] = splitmix64_stream(0x5EED0000 + j, d)
+            cap_one = np.empty((1 << cap_h, 4), dtype=np.uint64)
+            h1 = C.c_void_p()
+            _ffi.check(L.pcs_commit_from_coeffs(_ffi.ptr_array([fn[j] for j in range(w)]), w, lg_d, r, cap_h, None, 0, 0,
+                                                _ffi.ptr(cap_one), C.byref(h1)))
+            L.pcs_batch_free(h1)
+            parity["cap_equal_to_single_gpu"] = bool(np.array_equal(cap_dev, cap_one))
+            parity["e2e_cap_equal_to_single_gpu"] = bool(np.array_equal(cap_host, cap_one)) if e2e is not None else None
+            del full, fn
+        dist.barrier()
+    parity["lg_d_sample"] = lg_s
+    out["parity_check"] = parity
+
+    # ---- BASELINE configs[4]: one 135 x 2^24 commitment over the whole box ----
+    if world > 1 and (a.large_commit == "on" or (a.large_commit == "auto" and world == 8 and lg_d == 20 and w == 135)):
+        out["large_commit"] = large_commit_bench(a, world, rank, dev, stream)
+
     if rank == 0:
         if not a.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(a)
-            # parity spot-check of the benchmark itself: same seeds at the CPU sample size
-            lg = min(a.cpu_sample_lg_d, a.lg_d)
-            from helpers import seeded_polys as sp
-            import oracle
-            small = sp(w, 1 << lg, base_seed=0x5EED0000)
-            b = pcs.PolynomialBatch.from_coeffs(small, r, False, cap_h)
-            ok = bool(np.array_equal(b.merkle_tree.cap.hashes, oracle.commit_from_coeffs(small, r, cap_h)["cap"]))
-            out["parity_check"] = {"cap_equal_to_oracle_at_sample_size": ok, "lg_d": lg}
-            b.free()
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -20,8 +20,12 @@
  *     The reference panics on invalid input; the Rust shim turns non-zero into panic!() with the
  *     reference's message.
  *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with PCS_ERR_CUDA.
- *   - One commit in flight per process (the reference's call sites are sequential:
- *     plonk/prover.rs:145,212,260; circuit_builder.rs:1021).
+ *   - Contexts: the engine keeps one context (stream, staging buffers, twiddle tables) per CUDA device.  The
+ *     single-device entry points act on the calling thread's CURRENT context = the device of its last pcs_init
+ *     (device 0 by default); a batch remembers the context that made it, so its accessors and pcs_batch_free run on the
+ *     right device whatever is current.  One call in flight per context (the reference's call sites are sequential:
+ *     plonk/prover.rs:145,212,260; circuit_builder.rs:1021); different contexts may be driven from different host
+ *     threads at the same time (that is how pcs_multi_* uses a whole box).
  */
 #ifndef PCS_H
 #define PCS_H
@@ -52,8 +56,7 @@ typedef enum {
 
 enum {
     PCS_DEVICE_PTRS = 1u << 0,   /* input polynomial pointers are device pointers (no H2D copy)         */
-    PCS_KEEP_COEFFS = 1u << 1,   /* keep the coefficient vectors on the device (PolynomialBatch.polynomials) */
-    PCS_NO_LDE_STORE = 1u << 2   /* reserved                                                            */
+    PCS_KEEP_COEFFS = 1u << 1    /* keep the coefficient vectors on the device (PolynomialBatch.polynomials) */
 };
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
@@ -61,6 +64,9 @@ enum {
  * `stream` may be NULL (the engine creates its own) or an existing cudaStream_t the caller owns
  * (e.g. torch's current stream) so that caller-side CUDA events time the engine's kernels. */
 PCS_API int pcs_init(int device, void* stream);
+/* The CUDA device of the calling thread's current context, or -1 before pcs_init. */
+PCS_API int pcs_device(void);
+/* Destroys every context (all devices) and the multi-GPU state; batches must have been freed. */
 PCS_API void pcs_shutdown(void);
 PCS_API const char* pcs_last_error(void);
 /* The cudaStream_t all engine work is enqueued on. */
@@ -68,6 +74,20 @@ PCS_API void* pcs_stream(void);
 PCS_API int pcs_synchronize(void);
 
 /* ---- primitives (unit-testable against the reference's own tests) ------------------------------ */
+/* Element-wise GoldilocksField arithmetic on the device: out[i] = a[i] (op) b[i], any u64 in, canonical out -- the
+ * device counterpart of the field grid test, field/src/prime_field_testing.rs:78-125.  b may be NULL for unary ops.  */
+typedef enum {
+    PCS_OP_ADD = 0,       /* goldilocks_field.rs:199-221                                              */
+    PCS_OP_SUB = 1,       /* :223-243                                                                 */
+    PCS_OP_MUL = 2,       /* :267-274, reduce128 :356-369 (the Poseidon kernels' reduction)           */
+    PCS_OP_MUL_MAD = 3,   /* the same product through the NTT kernels' multiply-add reduction         */
+    PCS_OP_SQUARE = 4,
+    PCS_OP_CANON = 5,     /* to_canonical_u64 :171-178                                                */
+    PCS_OP_NEG = 6,       /* :245-255                                                                 */
+    PCS_OP_REDUCE96 = 7,  /* a + (b mod 2^32) * 2^64, reduce96 :347-354                               */
+    PCS_OP_MUL_2EXP = 8   /* a * 2^b                                                                  */
+} pcs_field_op_kind;
+PCS_API int pcs_field_op(int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);
 /* Poseidon::poseidon on n states, in place.                      plonky2/src/hash/poseidon.rs:599-609 */
 PCS_API int pcs_poseidon_permute(uint64_t* states /*[n][12]*/, size_t n);
 /* fri_proof_of_work: smallest witness w in 0..p-1 such that, with w written to lane `witness_pos` of the duplex
@@ -138,10 +158,20 @@ PCS_API int pcs_commit_shard_from_coeffs(const uint64_t* const* polys, size_t w,
  * peer memory): begin allocates the shard, every extend runs the coset LDE of polynomials [poly_first, poly_first+count)
  * asynchronously on pcs_stream() -- e.g. while the next chunk of an all-gather or H2D copy is still in flight -- and
  * finish hashes the leaves, builds the subtrees and returns the local cap.  Every polynomial must be supplied once. */
-PCS_API int pcs_shard_begin(size_t w, unsigned lg_d, unsigned rate_bits, unsigned coset_first, unsigned lg_cosets,
+PCS_API int pcs_shard_begin(size_t w, size_t salt_w, unsigned lg_d, unsigned rate_bits, unsigned coset_first, unsigned lg_cosets,
                     unsigned local_cap_height, pcs_batch** out);
 PCS_API int pcs_shard_extend(pcs_batch* b, size_t poly_first, size_t count, const uint64_t* const* polys_dev);
 PCS_API int pcs_shard_finish(pcs_batch* b, uint64_t* cap_out /*NULL or [2^local_cap_height][4]*/);
+/* A shard whose LDE rows are computed ELSEWHERE -- the north-star's other partition: every GPU extends its own block of
+ * polynomials over all cosets and the rows travel (all-to-all over NVLink) to the GPU that hashes their leaf range.
+ * `width` columns (the last salt_w of them salts) of 2^lg_n leaves; fill them with pcs_shard_set_rows or write them in
+ * place at pcs_batch_lde_dev(b) + row * 2^lg_n, then pcs_shard_finish.  Leaf ranges need not be whole cosets, so this
+ * form also serves more GPUs than 2^rate_bits.                                                                     */
+PCS_API int pcs_shard_begin_rows(size_t width, size_t salt_w, unsigned lg_n, unsigned local_cap_height, pcs_batch** out);
+/* Rows [row_first, row_first + count) of a begun shard <- count DEVICE pointers to 2^lg_n values each, already in LEAF
+ * order (salt columns of a shard: row_first = w; received LDE rows).  canonical != 0: the values are known to be < p
+ * (the engine's own LDE output) and are not canonicalised again.  Asynchronous on pcs_stream().                    */
+PCS_API int pcs_shard_set_rows(pcs_batch* b, size_t row_first, size_t count, const uint64_t* const* rows_dev, int canonical);
 /* PolynomialBatch::from_values: IFFT every column first.                         oracle.rs:43-65
  *   coeffs_out : NULL, or w host pointers receiving the d coefficients of each polynomial
  *                (the reference keeps them as `polynomials`).                                      */
@@ -184,6 +214,44 @@ PCS_API void pcs_batch_free(pcs_batch* b);
  * reset, and how many batches that was; lets a caller free each batch immediately (so the next
  * commit reuses its HBM) and still read per-kernel times afterwards.  Synchronises the stream. */
 PCS_API int pcs_timing_totals(float ms[5], unsigned* n_commits, int reset);
+
+/* ---- one commitment over several GPUs of this box from ONE host process -----------------------------
+ * The reference's caller is a single Rust thread (prove(), plonk/prover.rs:145,212,260); these entry points let it use a
+ * whole 8 x B200 box without a process per GPU: the library keeps a context and a worker thread per device, device g
+ * extends and hashes the coset blocks [g 2^r / G, (g+1) 2^r / G) (= a contiguous leaf range = whole cap subtrees), and the
+ * coefficient exchange is fused into the first NTT pass, which reads the other devices' blocks over NVLink in place.
+ * Results are bit-identical to pcs_commit_from_* on one GPU.  n_devices: a power of two, <= 2^rate_bits.            */
+typedef struct pcs_multi_batch pcs_multi_batch;
+/* devices == NULL: the first n_devices visible devices (all of them, rounded down to a power of two, when n_devices <= 0). */
+PCS_API int pcs_multi_init(const int* devices, int n_devices);
+/* Number of devices of the multi-GPU state (0 before pcs_multi_init); fills `devices` when not NULL.                  */
+PCS_API int pcs_multi_devices(int* devices);
+/* PolynomialBatch::from_coeffs over the devices of pcs_multi_init.  polys: HOST pointers (pageable or pinned; every
+ * device copies its share of each chunk over its own PCIe link while the previous chunk is being extended), or with
+ * PCS_DEVICE_PTRS device pointers on ANY of the devices (read in place, over NVLink where remote).  salts: NULL or salt_w
+ * pointers to N values each in natural LDE order, as in pcs_commit_from_coeffs.  Synchronous.                         */
+PCS_API int pcs_multi_commit_from_coeffs(const uint64_t* const* polys, size_t w, unsigned lg_d, unsigned rate_bits,
+                                 unsigned cap_height, const uint64_t* const* salts, size_t salt_w, unsigned flags,
+                                 uint64_t* cap_out, pcs_multi_batch** out);
+/* PolynomialBatch::from_values: every device IFFTs its own block of the polynomials first (oracle.rs:51-55).          */
+PCS_API int pcs_multi_commit_from_values(const uint64_t* const* values, size_t w, unsigned lg_d, unsigned rate_bits,
+                                 unsigned cap_height, const uint64_t* const* salts, size_t salt_w, unsigned flags,
+                                 uint64_t* const* coeffs_out, uint64_t* cap_out, pcs_multi_batch** out);
+PCS_API int pcs_multi_batch_shape(const pcs_multi_batch* b, size_t* n_leaves, size_t* leaf_len, int* n_shards, unsigned* cap_height);
+PCS_API int pcs_multi_batch_cap(const pcs_multi_batch* b, uint64_t* cap /*[2^cap_height][4]*/);
+/* merkle_tree.leaves[i] / MerkleTree::prove(i) for GLOBAL leaf indices, served by the device that owns the leaf; above a
+ * device's root (n_devices > 2^cap_height) the path continues through the other devices' roots.                      */
+PCS_API int pcs_multi_batch_get_rows(const pcs_multi_batch* b, const uint64_t* leaf_indices, size_t n, uint64_t* rows);
+PCS_API int pcs_multi_batch_prove(const pcs_multi_batch* b, size_t leaf_index, uint64_t* siblings /*[log2 N - cap_height][4]*/);
+/* The shard of device i as a plain batch (leaf indices relative to the shard; its digests are the contiguous slice
+ * [i * n_digests / G ..] of the reference's `digests` when G <= 2^cap_height).  Owned by the multi batch.             */
+PCS_API pcs_batch* pcs_multi_batch_shard(const pcs_multi_batch* b, int i);
+/* Device address of every polynomial's coefficient vector (needs PCS_KEEP_COEFFS, from_values or PCS_DEVICE_PTRS inputs):
+ * what pcs_eval_ext_dev / pcs_fri_final_poly_dev read, from any device of the group.                                  */
+PCS_API int pcs_multi_batch_poly_ptrs(const pcs_multi_batch* b, const uint64_t** ptrs /*[w]*/);
+/* Phase times as in pcs_batch_timings, maximum over the devices.                                                      */
+PCS_API int pcs_multi_batch_timings(const pcs_multi_batch* b, float ms[5]);
+PCS_API void pcs_multi_batch_free(pcs_multi_batch* b);
 
 /* ---- FRI opening proof on the device: the consumers of a committed batch's coefficients ------------
  * Extension elements are F::Extension = QuadraticExtension<GoldilocksField> = [u64; 2] = a + b*X, X^2 = 7

@@ -67,6 +67,8 @@ def lib():
         L.ref_poly_eval.argtypes = [u64p, sz, u64]
         L.ref_poly_eval.restype = u64
         L.ref_num_threads.restype = i32
+        L.ref_set_num_threads.argtypes = [i32]
+        L.ref_set_num_threads.restype = None
     return _lib
 
 
@@ -81,6 +83,21 @@ def _arr(a, copy=False):
 
 def num_threads():
     return lib().ref_num_threads()
+
+
+def set_num_threads(n):
+    """Override OMP_NUM_THREADS (torchrun sets it to 1 for its children)."""
+    lib().ref_set_num_threads(int(n))
+    return num_threads()
+
+
+def use_all_cores():
+    """All host cores this process may run on, whatever OMP_NUM_THREADS says."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return set_num_threads(n)
 
 
 # ---- field --------------------------------------------------------------------------------

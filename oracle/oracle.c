@@ -526,5 +526,15 @@ API int ref_num_threads(void) {
 #endif
 }
 
+/* Thread count of the OpenMP loops (the reference uses the global rayon pool = all cores, maybe_rayon/src/lib.rs).
+ * torchrun exports OMP_NUM_THREADS=1 to its children: bench.py's reference arm overrides that here. */
+API void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* FRI opening proof arithmetic */
 #include "fri.c"

@@ -18,10 +18,12 @@ PCS_KEEP_COEFFS = 2
 # every symbol include/pcs.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "pcs_init": (C.c_int, [C.c_int, C.c_void_p]),
+    "pcs_device": (C.c_int, []),
     "pcs_shutdown": (None, []),
     "pcs_last_error": (C.c_char_p, []),
     "pcs_stream": (C.c_void_p, []),
     "pcs_synchronize": (C.c_int, []),
+    "pcs_field_op": (C.c_int, [C.c_int, u64p, u64p, sz, u64p]),
     "pcs_poseidon_permute": (C.c_int, [u64p, sz]),
     "pcs_pow_grind": (C.c_int, [u64p, C.c_uint, C.c_uint, u64p]),
     "pcs_hash_or_noop": (C.c_int, [u64p, sz, sz, u64p]),
@@ -34,7 +36,9 @@ SIGNATURES = {
     "pcs_merkle_build": (C.c_int, [u64p, sz, sz, C.c_uint, u64p, u64p]),
     "pcs_commit_from_coeffs": (C.c_int, [u64pp, sz, C.c_uint, C.c_uint, C.c_uint, u64pp, sz, C.c_uint, u64p, C.POINTER(C.c_void_p)]),
     "pcs_commit_shard_from_coeffs": (C.c_int, [u64pp, sz, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, u64pp, sz, C.c_uint, u64p, C.POINTER(C.c_void_p)]),
-    "pcs_shard_begin": (C.c_int, [sz, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_void_p)]),
+    "pcs_shard_begin": (C.c_int, [sz, sz, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_void_p)]),
+    "pcs_shard_begin_rows": (C.c_int, [sz, sz, C.c_uint, C.c_uint, C.POINTER(C.c_void_p)]),
+    "pcs_shard_set_rows": (C.c_int, [C.c_void_p, sz, sz, u64pp, C.c_int]),
     "pcs_shard_extend": (C.c_int, [C.c_void_p, sz, sz, u64pp]),
     "pcs_shard_finish": (C.c_int, [C.c_void_p, u64p]),
     "pcs_commit_from_values": (C.c_int, [u64pp, sz, C.c_uint, C.c_uint, C.c_uint, u64pp, sz, C.c_uint, u64pp, u64p, C.POINTER(C.c_void_p)]),
@@ -54,6 +58,19 @@ SIGNATURES = {
     "pcs_batch_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "pcs_batch_free": (None, [C.c_void_p]),
     "pcs_timing_totals": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_uint), C.c_int]),
+    # one commitment over several GPUs from one process
+    "pcs_multi_init": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
+    "pcs_multi_devices": (C.c_int, [C.POINTER(C.c_int)]),
+    "pcs_multi_commit_from_coeffs": (C.c_int, [u64pp, sz, C.c_uint, C.c_uint, C.c_uint, u64pp, sz, C.c_uint, u64p, C.POINTER(C.c_void_p)]),
+    "pcs_multi_commit_from_values": (C.c_int, [u64pp, sz, C.c_uint, C.c_uint, C.c_uint, u64pp, sz, C.c_uint, u64pp, u64p, C.POINTER(C.c_void_p)]),
+    "pcs_multi_batch_shape": (C.c_int, [C.c_void_p, C.POINTER(sz), C.POINTER(sz), C.POINTER(C.c_int), C.POINTER(C.c_uint)]),
+    "pcs_multi_batch_cap": (C.c_int, [C.c_void_p, u64p]),
+    "pcs_multi_batch_get_rows": (C.c_int, [C.c_void_p, u64p, sz, u64p]),
+    "pcs_multi_batch_prove": (C.c_int, [C.c_void_p, sz, u64p]),
+    "pcs_multi_batch_shard": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "pcs_multi_batch_poly_ptrs": (C.c_int, [C.c_void_p, u64pp]),
+    "pcs_multi_batch_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "pcs_multi_batch_free": (None, [C.c_void_p]),
     # FRI opening proof
     "pcs_batch_eval_ext": (C.c_int, [C.c_void_p, u64p, u64p]),
     "pcs_eval_ext_dev": (C.c_int, [u64pp, sz, C.c_uint, u64p, u64p]),

@@ -2,6 +2,7 @@
 // PolynomialBatch::from_coeffs / from_values path (plonky2/src/fri/oracle.rs:43-98) and the
 // accessors the reference's consumers need.  No CPU fallback anywhere in this file.
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -36,9 +37,28 @@ struct Ctx {
     void* ring[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ring_ev[3] = {nullptr, nullptr, nullptr};   // the DMA out of the slot has finished
     bool ring_busy[3] = {false, false, false};
+    unsigned next_slot = 0;
 };
-static Ctx g_ctx;
+// One context per CUDA device (created by pcs_init / pcs_multi_init, destroyed by pcs_shutdown).  The single-device
+// entry points work on the calling thread's CURRENT context (the device of its last pcs_init, device 0 by default); a
+// batch remembers the context that made it, so accessors and pcs_batch_free act on the right device and stream whatever
+// is current.  One call in flight per context; different contexts may be driven from different host threads.
+constexpr int MAX_DEVICES = 64;
+static Ctx g_none;                                   // never initialised: what a thread sees before pcs_init
+static Ctx* g_ctxs[MAX_DEVICES] = {nullptr};
+static std::mutex g_ctx_mutex;
+static thread_local Ctx* g_cur = &g_none;
+#define g_ctx (*g_cur)
 
+// make `c` current on this thread (device included); returns the previous one
+static Ctx* ctx_enter(Ctx* c) {
+    Ctx* prev = g_cur;
+    if (c && c != g_cur) {
+        g_cur = c;
+        cudaSetDevice(c->device);
+    }
+    return prev;
+}
 // fold completed/pending event sets into the running totals (caller has synchronised the stream)
 static void drain_pending() {
     for (auto& pe : g_ctx.pending) {
@@ -60,11 +80,24 @@ int fail(int code, const std::string& msg) {
     return code;
 }
 
+BatchScope::BatchScope(const pcs_batch* b) : prev(g_cur) {
+    if (b && b->ctx) ctx_enter((Ctx*)b->ctx);
+}
+BatchScope::~BatchScope() { ctx_enter((Ctx*)prev); }
+
+pcs_batch* batch_new() {
+    pcs_batch* b = batch_new();
+    b->ctx = g_cur;
+    return b;
+}
+
 #define PCS_NEED_INIT()                                                            \
     do {                                                                           \
         if (!g_ctx.init) {                                                         \
             int _rc = pcs_init(-1, nullptr);                                       \
             if (_rc) return _rc;                                                   \
+        } else {                                                                   \
+            cudaSetDevice(g_ctx.device); /* the caller (torch ...) may have switched this thread's device */ \
         }                                                                          \
     } while (0)
 
@@ -87,6 +120,32 @@ extern "C" {
 
 const char* pcs_last_error(void) { return g_err.c_str(); }
 
+static int ctx_create(int device, void* stream, Ctx** out) {
+    PCS_CUDA(cudaSetDevice(device));
+    Ctx* c = new Ctx();
+    c->device = device;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+        c->own_stream = false;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete c;
+            return fail(PCS_ERR_CUDA, std::string("cudaStreamCreateWithFlags: ") + cudaGetErrorString(e));
+        }
+        c->own_stream = true;
+    }
+    // keep freed blocks cached in the pool: commits reuse multi-GB buffers
+    cudaMemPool_t pool;
+    uint64_t thr = UINT64_MAX;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    cudaGetLastError();
+    c->init = true;
+    *out = c;
+    return PCS_OK;
+}
+
 int pcs_init(int device, void* stream) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -97,50 +156,59 @@ int pcs_init(int device, void* stream) {
         if (g_ctx.init) return PCS_OK;
         device = 0;
     }
-    if (g_ctx.init && (g_ctx.device != device)) pcs_shutdown();
+    if (device >= count || device >= MAX_DEVICES)
+        return fail(PCS_ERR_ARG, "device " + std::to_string(device) + " out of range (" + std::to_string(count) + " visible)");
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    Ctx* c = g_ctxs[device];
+    if (!c) {
+        int rc = ctx_create(device, stream, &c);
+        if (rc) return rc;
+        g_ctxs[device] = c;
+    } else if (stream && stream != (void*)c->stream) {
+        // re-bind the stream only; work already enqueued on the old stream must be finished first (twiddle tables,
+        // batches) because nothing orders the new stream behind it
+        cudaSetDevice(device);
+        cudaStreamSynchronize(c->stream);
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+        c->stream = (cudaStream_t)stream;
+        c->own_stream = false;
+    }
+    ctx_enter(c);                      // current for this thread; other devices' contexts (and their batches) stay alive
     PCS_CUDA(cudaSetDevice(device));
-    if (g_ctx.init) {
-        // re-bind the stream only
-        if (stream && stream != (void*)g_ctx.stream) {
-            if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.stream);
-            g_ctx.stream = (cudaStream_t)stream;
-            g_ctx.own_stream = false;
-        }
-        return PCS_OK;
-    }
-    g_ctx.device = device;
-    if (stream) {
-        g_ctx.stream = (cudaStream_t)stream;
-        g_ctx.own_stream = false;
-    } else {
-        PCS_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
-        g_ctx.own_stream = true;
-    }
-    // keep freed blocks cached in the pool: commits reuse multi-GB buffers
-    cudaMemPool_t pool;
-    PCS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thr = UINT64_MAX;
-    PCS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    g_ctx.init = true;
     return PCS_OK;
 }
 
-void pcs_shutdown(void) {
-    if (!g_ctx.init) return;
-    cudaStreamSynchronize(g_ctx.stream);
+int pcs_device(void) { return g_ctx.init ? g_ctx.device : -1; }
+
+static void ctx_destroy(Ctx* c) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    g_cur = c;
     drain_pending();
-    ntt_plans_free();
-    if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
-    if (g_ctx.pin_in) cudaFreeHost(g_ctx.pin_in);
-    if (g_ctx.pin_out) cudaFreeHost(g_ctx.pin_out);
-    if (g_ctx.ev_sync) cudaEventDestroy(g_ctx.ev_sync);
-    for (auto& e : g_ctx.chunk_ev) cudaEventDestroy(e);
-    for (auto& r : g_ctx.ring)
+    ntt_plans_free();                  // this device's twiddle tables
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->pin_in) cudaFreeHost(c->pin_in);
+    if (c->pin_out) cudaFreeHost(c->pin_out);
+    if (c->ev_sync) cudaEventDestroy(c->ev_sync);
+    for (auto& e : c->chunk_ev) cudaEventDestroy(e);
+    for (auto& r : c->ring)
         if (r) cudaFreeHost(r);
-    for (auto& e : g_ctx.ring_ev)
+    for (auto& e : c->ring_ev)
         if (e) cudaEventDestroy(e);
-    if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.stream);
-    g_ctx = Ctx();
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void pcs_shutdown(void) {
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    multi_shutdown_locked();
+    for (auto& c : g_ctxs)
+        if (c) {
+            ctx_destroy(c);
+            c = nullptr;
+        }
+    g_cur = &g_none;
+    cudaGetLastError();
 }
 
 void* pcs_stream(void) { return g_ctx.init ? (void*)g_ctx.stream : nullptr; }
@@ -154,6 +222,28 @@ int pcs_synchronize(void) {
 // ------------------------------------------------------------------------------------------------
 // primitives
 // ------------------------------------------------------------------------------------------------
+int pcs_field_op(int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
+    PCS_NEED_INIT();
+    if (n == 0) return PCS_OK;
+    if (!a || !out) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (op < PCS_OP_ADD || op > PCS_OP_MUL_2EXP) return fail(PCS_ERR_ARG, "unknown field operation");
+    const bool binary = op != PCS_OP_SQUARE && op != PCS_OP_CANON && op != PCS_OP_NEG;
+    if (binary && !b) return fail(PCS_ERR_ARG, "second operand is NULL");
+    cudaStream_t st = g_ctx.stream;
+    DevBuf da, db, dout;
+    PCS_CUDA(da.alloc(n * 8, st));
+    PCS_CUDA(dout.alloc(n * 8, st));
+    PCS_CUDA(cudaMemcpyAsync(da.p, a, n * 8, cudaMemcpyHostToDevice, st));
+    if (binary) {
+        PCS_CUDA(db.alloc(n * 8, st));
+        PCS_CUDA(cudaMemcpyAsync(db.p, b, n * 8, cudaMemcpyHostToDevice, st));
+    }
+    PCS_CUDA(launch_field_op(op, da.u64(), binary ? db.u64() : nullptr, n, dout.u64(), st));
+    PCS_CUDA(cudaMemcpyAsync(out, dout.p, n * 8, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
 int pcs_poseidon_permute(uint64_t* states, size_t n) {
     PCS_NEED_INIT();
     if (n == 0) return PCS_OK;
@@ -305,6 +395,8 @@ int pcs_ntt_dev(uint64_t* polys_dev, size_t w, unsigned lg_n, int inverse) {
     return PCS_OK;   // asynchronous on pcs_stream()
 }
 
+}  // extern "C"
+
 constexpr size_t SMALL_POLY_BYTES = 32 * 1024;     // below this, host polynomials go through pinned staging
 constexpr size_t PIN_STAGING_MAX = 64u << 20;
 
@@ -349,12 +441,11 @@ static void gather_bytes(char* dst, const uint64_t* const* polys, size_t bytes_e
 // Send `count` pageable host polynomials (d elements each) to the contiguous device block `dst` through the pinned
 // ring: pieces of <= RING_SLOT_BYTES are gathered by STAGE_THREADS host threads and leave with one DMA each on the
 // copy stream; the gather of piece p + 1 overlaps the DMA of piece p.
-static int stage_pageable(const uint64_t* const* polys, size_t count, size_t d, uint64_t* dst, cudaStream_t copy_st) {
+int pcs::stage_pageable(const uint64_t* const* polys, size_t count, size_t d, uint64_t* dst, cudaStream_t copy_st) {
     const size_t bytes_each = d * 8, total = count * bytes_each;
-    static unsigned next_slot = 0;
     for (size_t off = 0; off < total; off += RING_SLOT_BYTES) {
         const size_t len = total - off < RING_SLOT_BYTES ? total - off : RING_SLOT_BYTES;
-        const unsigned sl = next_slot++ % 3;
+        const unsigned sl = g_ctx.next_slot++ % 3;
         if (!g_ctx.ring[sl]) {
             PCS_CUDA(cudaHostAlloc(&g_ctx.ring[sl], RING_SLOT_BYTES, cudaHostAllocDefault));
             PCS_CUDA(cudaEventCreateWithFlags(&g_ctx.ring_ev[sl], cudaEventDisableTiming));
@@ -388,6 +479,8 @@ static int stage_polys(const uint64_t* const* polys, size_t w, size_t d, bool de
     }
     return PCS_OK;
 }
+
+extern "C" {
 
 int pcs_coset_lde(const uint64_t* const* coeffs, size_t w, unsigned lg_d, unsigned rate_bits, uint64_t shift,
                   uint64_t* out, int layout) {
@@ -481,6 +574,7 @@ int pcs_merkle_build(const uint64_t* leaves, size_t n, size_t len, unsigned cap_
 // ------------------------------------------------------------------------------------------------
 void pcs_batch_free(pcs_batch* b) {
     if (!b) return;
+    BatchScope scope(b);
     cudaStream_t st = g_ctx.stream;
     if (b->coeffs) cudaFreeAsync(b->coeffs, st);
     if (b->lde) cudaFreeAsync(b->lde, st);
@@ -530,11 +624,21 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
     NttPlan* iplan = from_values ? ntt_plan_get(lg_d, 0, true, 1, st) : nullptr;
     if (!plan || (from_values && !iplan)) return fail(PCS_ERR_ALLOC, "twiddle table allocation failed");
 
-    pcs_batch* b = new pcs_batch();
+    pcs_batch* b = batch_new();
     b->w = w; b->salt_w = salt_w; b->lg_d = lg_d; b->rate_bits = lg_cosets; b->cap_height = cap_height;
     b->full_rate_bits = rate_bits; b->coset_first = coset_first;
     b->n = n; b->n_digests = 2 * (n - n_cap); b->has_ifft = from_values;
     struct Guard { pcs_batch* b; bool armed = true; ~Guard() { if (armed) pcs_batch_free(b); } } guard{b};
+    // Declared after `guard`, so destroyed before it: on every failure exit taken once H2D copies were enqueued on the copy
+    // stream, wait for them before the guard returns their destination to the pool (and release the pinned ring slots).
+    struct CopyDrain {
+        bool armed = false;
+        ~CopyDrain() {
+            if (!armed || !g_ctx.copy_stream) return;
+            cudaStreamSynchronize(g_ctx.copy_stream);
+            for (auto& busy : g_ctx.ring_busy) busy = false;
+        }
+    } copy_drain;
     for (auto& e : b->ev) PCS_CUDA(cudaEventCreate(&e));
     PCS_CUDA(cudaMallocAsync((void**)&b->lde, wt * n * 8, st));
     PCS_CUDA(cudaMallocAsync((void**)&b->digests, b->n_digests ? b->n_digests * 32 : 32, st));
@@ -593,6 +697,7 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
             }
             PCS_CUDA(cudaEventRecord(g_ctx.ev_sync, st));               // `staged` exists from here on
             PCS_CUDA(cudaStreamWaitEvent(g_ctx.copy_stream, g_ctx.ev_sync, 0));
+            copy_drain.armed = true;
             for (size_t k = 0; k < n_chunks && !pageable; k++) {
                 size_t j0 = k * H2D_CHUNK, j1 = j0 + H2D_CHUNK < w ? j0 + H2D_CHUNK : w;
                 int rc = stage_polys(polys + j0, j1 - j0, d, false, staged + j0 * d, g_ctx.copy_stream);
@@ -692,6 +797,7 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
         for (size_t j = 0; j < w; j++)
             if (coeffs_out[j]) memcpy(coeffs_out[j], (char*)g_ctx.pin_out + j * d * 8, d * 8);
     guard.armed = false;
+    copy_drain.armed = false;   // the main stream waited on every chunk event and has been synchronised (host inputs)
     b->committed = true;
     *out = b;
     return PCS_OK;
@@ -712,7 +818,7 @@ int pcs_commit_shard_from_coeffs(const uint64_t* const* polys, size_t w, unsigne
 }
 
 // ---- streaming shard commit: the polynomials arrive in groups (e.g. chunks of an all-gather still in flight) ----
-int pcs_shard_begin(size_t w, unsigned lg_d, unsigned rate_bits, unsigned coset_first, unsigned lg_cosets,
+int pcs_shard_begin(size_t w, size_t salt_w, unsigned lg_d, unsigned rate_bits, unsigned coset_first, unsigned lg_cosets,
                     unsigned local_cap_height, pcs_batch** out) {
     PCS_NEED_INIT();
     if (!out) return fail(PCS_ERR_ARG, "out is NULL");
@@ -728,13 +834,13 @@ int pcs_shard_begin(size_t w, unsigned lg_d, unsigned rate_bits, unsigned coset_
     cudaStream_t st = g_ctx.stream;
     if (!ntt_plan_get(lg_d, rate_bits, false, 7, st)) return fail(PCS_ERR_ALLOC, "twiddle table allocation failed");
     const size_t n = (size_t)1 << lg_n, n_cap = (size_t)1 << local_cap_height;
-    pcs_batch* b = new pcs_batch();
-    b->w = w; b->lg_d = lg_d; b->rate_bits = lg_cosets; b->cap_height = local_cap_height;
+    pcs_batch* b = batch_new();
+    b->w = w; b->salt_w = salt_w; b->lg_d = lg_d; b->rate_bits = lg_cosets; b->cap_height = local_cap_height;
     b->full_rate_bits = rate_bits; b->coset_first = coset_first;
     b->n = n; b->n_digests = 2 * (n - n_cap);
     struct Guard { pcs_batch* b; bool armed = true; ~Guard() { if (armed) pcs_batch_free(b); } } guard{b};
     for (auto& e : b->ev) PCS_CUDA(cudaEventCreate(&e));
-    PCS_CUDA(cudaMallocAsync((void**)&b->lde, w * n * 8, st));
+    PCS_CUDA(cudaMallocAsync((void**)&b->lde, (w + salt_w) * n * 8, st));
     PCS_CUDA(cudaMallocAsync((void**)&b->digests, b->n_digests ? b->n_digests * 32 : 32, st));
     PCS_CUDA(cudaMallocAsync((void**)&b->cap, n_cap * 32, st));
     PCS_CUDA(cudaEventRecord(b->ev[0], st));
@@ -744,10 +850,60 @@ int pcs_shard_begin(size_t w, unsigned lg_d, unsigned rate_bits, unsigned coset_
     return PCS_OK;
 }
 
+// A tree shard whose LDE rows are computed elsewhere (another GPU's LDE arriving over NVLink: the north-star's
+// polynomial-partitioned LDE + all-to-all): `width` rows of 2^lg_n leaves each, filled through pcs_shard_set_rows or written
+// in place at pcs_batch_lde_dev() + row * 2^lg_n, then pcs_shard_finish.
+int pcs_shard_begin_rows(size_t width, size_t salt_w, unsigned lg_n, unsigned local_cap_height, pcs_batch** out) {
+    PCS_NEED_INIT();
+    if (!out) return fail(PCS_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (width == 0) return fail(PCS_ERR_ARG, "empty batch (oracle.rs:76 polynomials[0])");
+    if (salt_w > width) return fail(PCS_ERR_ARG, "more salt columns than columns");
+    if (lg_n > 32) return fail(PCS_ERR_TWO_ADICITY, "n_log <= TWO_ADICITY violated");
+    if (local_cap_height > lg_n)
+        return fail(PCS_ERR_CAP_HEIGHT, "cap_height=" + std::to_string(local_cap_height) +
+                                            " should be at most log2(leaves.len())=" + std::to_string(lg_n));
+    cudaStream_t st = g_ctx.stream;
+    const size_t n = (size_t)1 << lg_n, n_cap = (size_t)1 << local_cap_height;
+    pcs_batch* b = batch_new();
+    b->w = width - salt_w; b->salt_w = salt_w; b->lg_d = lg_n; b->rate_bits = 0; b->cap_height = local_cap_height;
+    b->full_rate_bits = 0; b->coset_first = 0; b->rows_only = true;
+    b->n = n; b->n_digests = 2 * (n - n_cap);
+    struct Guard { pcs_batch* b; bool armed = true; ~Guard() { if (armed) pcs_batch_free(b); } } guard{b};
+    for (auto& e : b->ev) PCS_CUDA(cudaEventCreate(&e));
+    PCS_CUDA(cudaMallocAsync((void**)&b->lde, width * n * 8, st));
+    PCS_CUDA(cudaMallocAsync((void**)&b->digests, b->n_digests ? b->n_digests * 32 : 32, st));
+    PCS_CUDA(cudaMallocAsync((void**)&b->cap, n_cap * 32, st));
+    PCS_CUDA(cudaEventRecord(b->ev[0], st));
+    PCS_CUDA(cudaEventRecord(b->ev[1], st));
+    guard.armed = false;
+    *out = b;
+    return PCS_OK;
+}
+
+int pcs_shard_set_rows(pcs_batch* b, size_t row_first, size_t count, const uint64_t* const* rows_dev, int canonical) {
+    if (!b || (count && !rows_dev)) return fail(PCS_ERR_ARG, "NULL pointer");
+    BatchScope scope(b);
+    if (b->committed) return fail(PCS_ERR_ARG, "batch already finished");
+    const size_t wt = b->w + b->salt_w;
+    if (row_first > wt || count > wt - row_first) return fail(PCS_ERR_ARG, "row range out of bounds");
+    cudaStream_t st = g_ctx.stream;
+    for (size_t k = 0; k < count; k++) {
+        if (!rows_dev[k]) return fail(PCS_ERR_ARG, "NULL row pointer");
+        uint64_t* dst = b->lde + (row_first + k) * b->n;
+        if (rows_dev[k] != dst)
+            PCS_CUDA(cudaMemcpyAsync(dst, rows_dev[k], b->n * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    if (!canonical && count) PCS_CUDA(launch_canonicalize(b->lde + row_first * b->n, count * b->n, st));
+    return PCS_OK;   // asynchronous on pcs_stream()
+}
+
 int pcs_shard_extend(pcs_batch* b, size_t poly_first, size_t count, const uint64_t* const* polys) {
+    BatchScope scope(b);
     if (!b || !polys) return fail(PCS_ERR_ARG, "NULL pointer");
     if (b->committed) return fail(PCS_ERR_ARG, "batch already finished");
-    if (poly_first + count > b->w) return fail(PCS_ERR_ARG, "polynomial range out of bounds");
+    if (b->rows_only) return fail(PCS_ERR_ARG, "this shard takes LDE rows (pcs_shard_set_rows), not polynomials");
+    if (poly_first > b->w || count > b->w - poly_first) return fail(PCS_ERR_ARG, "polynomial range out of bounds");
     if (count == 0) return PCS_OK;
     cudaStream_t st = g_ctx.stream;
     const size_t d = (size_t)1 << b->lg_d;
@@ -778,12 +934,13 @@ int pcs_shard_extend(pcs_batch* b, size_t poly_first, size_t count, const uint64
 }
 
 int pcs_shard_finish(pcs_batch* b, uint64_t* cap_out) {
+    BatchScope scope(b);
     if (!b) return fail(PCS_ERR_ARG, "NULL pointer");
     if (b->committed) return fail(PCS_ERR_ARG, "batch already finished");
     cudaStream_t st = g_ctx.stream;
     PCS_CUDA(cudaEventRecord(b->ev[2], st));
     PCS_CUDA(cudaEventRecord(b->ev[3], st));
-    int rc = build_tree_dev(b->lde, b->n, b->w, b->lg_d + b->rate_bits, b->cap_height, b->digests, b->cap, st, b->ev[4]);
+    int rc = build_tree_dev(b->lde, b->n, b->w + b->salt_w, b->lg_d + b->rate_bits, b->cap_height, b->digests, b->cap, st, b->ev[4]);
     if (rc) return rc;
     PCS_CUDA(cudaEventRecord(b->ev[5], st));
     b->committed = true;
@@ -810,6 +967,7 @@ int pcs_batch_shape(const pcs_batch* b, size_t* n_leaves, size_t* leaf_len, size
 }
 
 int pcs_batch_cap(const pcs_batch* b, uint64_t* cap) {
+    BatchScope scope(b);
     if (!b || !cap) return fail(PCS_ERR_ARG, "NULL pointer");
     cudaStream_t st = g_ctx.stream;
     PCS_CUDA(cudaMemcpyAsync(cap, b->cap, ((size_t)32) << b->cap_height, cudaMemcpyDeviceToHost, st));
@@ -818,6 +976,7 @@ int pcs_batch_cap(const pcs_batch* b, uint64_t* cap) {
 }
 
 int pcs_batch_digests(const pcs_batch* b, uint64_t* digests) {
+    BatchScope scope(b);
     if (!b) return fail(PCS_ERR_ARG, "NULL pointer");
     if (b->n_digests == 0) return PCS_OK;
     if (!digests) return fail(PCS_ERR_ARG, "NULL pointer");
@@ -828,8 +987,9 @@ int pcs_batch_digests(const pcs_batch* b, uint64_t* digests) {
 }
 
 int pcs_batch_leaves(const pcs_batch* b, size_t first, size_t count, uint64_t* rows) {
+    BatchScope scope(b);
     if (!b || !rows) return fail(PCS_ERR_ARG, "NULL pointer");
-    if (first + count > b->n) return fail(PCS_ERR_ARG, "leaf range out of bounds");
+    if (first > b->n || count > b->n - first) return fail(PCS_ERR_ARG, "leaf range out of bounds");
     if (count == 0) return PCS_OK;
     cudaStream_t st = g_ctx.stream;
     size_t wt = b->w + b->salt_w;
@@ -847,6 +1007,7 @@ int pcs_batch_leaves(const pcs_batch* b, size_t first, size_t count, uint64_t* r
 }
 
 int pcs_batch_get_rows(const pcs_batch* b, const uint64_t* leaf_indices, size_t n, uint64_t* rows) {
+    BatchScope scope(b);
     if (!b || (n && (!leaf_indices || !rows))) return fail(PCS_ERR_ARG, "NULL pointer");
     if (n == 0) return PCS_OK;
     for (size_t k = 0; k < n; k++)
@@ -864,6 +1025,7 @@ int pcs_batch_get_rows(const pcs_batch* b, const uint64_t* leaf_indices, size_t 
 }
 
 int pcs_batch_prove(const pcs_batch* b, size_t leaf_index, uint64_t* siblings) {
+    BatchScope scope(b);
     if (!b) return fail(PCS_ERR_ARG, "NULL pointer");
     if (leaf_index >= b->n) return fail(PCS_ERR_ARG, "leaf index out of bounds");
     unsigned lg_sub = b->lg_d + b->rate_bits - b->cap_height;
@@ -879,6 +1041,7 @@ int pcs_batch_prove(const pcs_batch* b, size_t leaf_index, uint64_t* siblings) {
 }
 
 int pcs_batch_prove_many(const pcs_batch* b, const uint64_t* leaf_indices, size_t n, uint64_t* siblings) {
+    BatchScope scope(b);
     if (!b || (n && !leaf_indices)) return fail(PCS_ERR_ARG, "NULL pointer");
     for (size_t k = 0; k < n; k++)
         if (leaf_indices[k] >= b->n) return fail(PCS_ERR_ARG, "leaf index out of bounds");
@@ -897,6 +1060,7 @@ int pcs_batch_prove_many(const pcs_batch* b, const uint64_t* leaf_indices, size_
 }
 
 int pcs_batch_coeffs(const pcs_batch* b, size_t poly, uint64_t* coeffs) {
+    BatchScope scope(b);
     if (!b || !coeffs) return fail(PCS_ERR_ARG, "NULL pointer");
     if (!b->coeffs) return fail(PCS_ERR_ARG, "coefficients were not kept (PCS_KEEP_COEFFS)");
     if (poly >= b->w) return fail(PCS_ERR_ARG, "polynomial index out of bounds");
@@ -908,6 +1072,7 @@ int pcs_batch_coeffs(const pcs_batch* b, size_t poly, uint64_t* coeffs) {
 }
 
 int pcs_batch_all_coeffs(const pcs_batch* b, uint64_t* coeffs) {
+    BatchScope scope(b);
     if (!b || !coeffs) return fail(PCS_ERR_ARG, "NULL pointer");
     if (!b->coeffs) return fail(PCS_ERR_ARG, "coefficients were not kept (PCS_KEEP_COEFFS)");
     cudaStream_t st = g_ctx.stream;
@@ -922,6 +1087,7 @@ const uint64_t* pcs_batch_digests_dev(const pcs_batch* b) { return b ? b->digest
 const uint64_t* pcs_batch_cap_dev(const pcs_batch* b) { return b ? b->cap : nullptr; }
 
 int pcs_batch_timings(const pcs_batch* b, float ms[5]) {
+    BatchScope scope(b);
     if (!b || !ms) return fail(PCS_ERR_ARG, "NULL pointer");
     PCS_CUDA(cudaStreamSynchronize(g_ctx.stream));
     for (int i = 0; i < 5; i++) PCS_CUDA(cudaEventElapsedTime(&ms[i], b->ev[i], b->ev[i + 1]));

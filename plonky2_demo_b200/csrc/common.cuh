@@ -22,6 +22,8 @@ struct pcs_batch {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool has_ifft = false;
     bool committed = false;  // all six events recorded
+    bool rows_only = false;  // pcs_shard_begin_rows: LDE rows are supplied, not computed here
+    void* ctx = nullptr;     // the per-device engine context (api.cu) that owns the buffers: accessors and free run there
 };
 
 namespace pcs {
@@ -40,6 +42,17 @@ void set_error(const std::string& msg);
 
 
 int fail(int code, const std::string& msg);   // set_error + return code
+// host polynomials (pageable memory) -> contiguous device block through the current context's pinned ring (api.cu)
+int stage_pageable(const uint64_t* const* polys, size_t count, size_t d, uint64_t* dst, cudaStream_t copy_st);
+void multi_shutdown_locked();                 // multi.cu: release the multi-GPU state (called by pcs_shutdown)
+pcs_batch* batch_new();                       // a batch bound to the calling thread's current context (api.cu)
+// Run on the context (device + stream) that owns `b`, whatever the calling thread's current one is; the caller's
+// context is restored on destruction (api.cu).
+struct BatchScope {
+    void* prev;
+    explicit BatchScope(const pcs_batch* b);
+    ~BatchScope();
+};
 
 // stream-ordered temporary buffer
 struct DevBuf {
@@ -95,6 +108,9 @@ cudaError_t launch_prove(const uint64_t* digests, unsigned lg_sub, size_t leaf_i
 cudaError_t launch_prove_many(const uint64_t* digests, unsigned lg_sub, const uint64_t* leaf_indices_dev, size_t n,
                               uint64_t* siblings, cudaStream_t st);
 
+// field_ops.cu: out[i] = a[i] (op) b[i]
+cudaError_t launch_field_op(int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------------
 // ntt.cu
 // ------------------------------------------------------------------------------------------------
@@ -121,6 +137,9 @@ cudaError_t ntt_inverse_bitrev(const NttPlan* plan, const uint64_t* values, size
 cudaError_t launch_bitrev_permute(const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride,
                                   size_t w, unsigned lg_n, cudaStream_t st, uint64_t scale = 1);
 uint64_t ntt_plan_scale(const NttPlan* plan);
+// out[i] = canon(in[brev_{lg_n}(first + i)]), i < count
+cudaError_t launch_bitrev_gather(const uint64_t* in, unsigned lg_n, size_t first, size_t count, uint64_t* out,
+                                 cudaStream_t st);
 // out[c][r] = in[r][c] for in [rows][cols] (row pitch in_pitch), out row pitch out_pitch
 cudaError_t launch_transpose(const uint64_t* in, size_t in_pitch, uint64_t* out, size_t out_pitch,
                              size_t rows, size_t cols, cudaStream_t st);

@@ -548,6 +548,7 @@ int pcs_batch_eval_ext(const pcs_batch* b, const uint64_t point[2], uint64_t* ou
     if (int rc = need_init()) return rc;
     if (!b || !point || !out) return fail(PCS_ERR_ARG, "NULL pointer");
     if (!b->coeffs) return fail(PCS_ERR_ARG, "coefficients were not kept (PCS_KEEP_COEFFS)");
+    BatchScope scope(b);
     return eval_ext_common(b->coeffs, nullptr, b->w, b->lg_d, point, out);
 }
 
@@ -685,6 +686,9 @@ int pcs_fri_final_poly(const pcs_batch* const* oracles, size_t n_oracles, size_t
         if (!oracles[o]->coeffs) return fail(PCS_ERR_ARG, "coefficients were not kept (PCS_KEEP_COEFFS)");
         if (oracles[o]->lg_d != oracles[0]->lg_d) return fail(PCS_ERR_ARG, "oracles of different degrees");
     }
+    for (size_t o = 1; o < n_oracles; o++)
+        if (oracles[o]->ctx != oracles[0]->ctx) return fail(PCS_ERR_ARG, "oracles live on different devices");
+    BatchScope scope(oracles[0]);
     const unsigned lg_d = oracles[0]->lg_d;
     const size_t d = (size_t)1 << lg_d;
     size_t total = 0;
@@ -772,7 +776,7 @@ int pcs_fri_commit_layer(const pcs_ext_poly* p, unsigned rate_bits, uint64_t shi
                                             " should be at most log2(leaves.len())=" + std::to_string(lg_leaves));
     const size_t n = (size_t)1 << lg_n, n_leaves = (size_t)1 << lg_leaves, width = (size_t)2 << arity_bits;
     const size_t n_cap = (size_t)1 << cap_height;
-    pcs_batch* b = new pcs_batch();
+    pcs_batch* b = batch_new();
     b->w = width; b->lg_d = lg_leaves; b->rate_bits = 0; b->full_rate_bits = 0; b->cap_height = cap_height;
     b->n = n_leaves; b->n_digests = 2 * (n_leaves - n_cap);
     struct Guard { pcs_batch* b; bool armed = true; ~Guard() { if (armed) pcs_batch_free(b); } } guard{b};

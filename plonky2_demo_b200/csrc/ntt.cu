@@ -33,10 +33,10 @@
 #include <tuple>
 #include <vector>
 
+#include <list>
+#include <mutex>
+
 #include "common.cuh"
-#ifndef PCS_REDUCE_MAD
-#define PCS_REDUCE_MAD 1   // NTT only: the butterfly is ALU-pipe bound, the multiply-add reduction trades 3 ALU ops for one IMAD.HI
-#endif
 #include "gl64.cuh"
 
 namespace pcs {
@@ -58,6 +58,16 @@ struct NttPlan {
     uint64_t shift;
     uint64_t scale;  // 1/d for the inverse transform (applied by the bit-reversal permutation that follows), else 1
     std::vector<NttPass> passes;
+    cudaEvent_t ready = nullptr;      // the table fill has finished (recorded on the stream that built the plan)
+    cudaStream_t built_on = nullptr;
+    int device = -1;
+    ~NttPlan() {
+        for (auto& ps : passes) {
+            if (ps.gamma) cudaFree(ps.gamma);
+            if (ps.psi) cudaFree(ps.psi);
+        }
+        if (ready) cudaEventDestroy(ready);
+    }
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -93,7 +103,18 @@ static uint64_t h_pow(uint64_t b, uint64_t e) {
     return acc;
 }
 
-static std::map<std::tuple<unsigned, unsigned, bool, uint64_t>, NttPlan*> g_plans;
+// Plan cache: one per CUDA device (twiddle tables live in that device's memory).  The commit path uses a handful of plans
+// (shift 7 and the inverse transform per degree); FRI layer shifts and caller-chosen shifts (pcs_coset_lde, pcs_coset_intt)
+// are arbitrary, so the cache is LRU-bounded.
+struct PlanCache {
+    typedef std::tuple<unsigned, unsigned, bool, uint64_t> Key;
+    std::list<std::pair<Key, NttPlan*>> lru;   // front = most recently used
+    std::map<Key, std::list<std::pair<Key, NttPlan*>>::iterator> index;
+};
+constexpr size_t NTT_MAX_PLANS = 48;
+constexpr int NTT_MAX_DEVICES = 64;
+static PlanCache g_plan_cache[NTT_MAX_DEVICES];
+static std::mutex g_plan_mutex;
 
 static std::vector<unsigned> split_stages(unsigned lg_d) {
     // equal-ish passes of at most NTT_MAX_NB stages; the FIRST pass gets the remainder so the
@@ -107,9 +128,20 @@ static std::vector<unsigned> split_stages(unsigned lg_d) {
 }
 
 NttPlan* ntt_plan_get(unsigned lg_d, unsigned r, bool inverse, uint64_t shift, cudaStream_t st) {
-    auto key = std::make_tuple(lg_d, r, inverse, shift);
-    auto it = g_plans.find(key);
-    if (it != g_plans.end()) return it->second;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= NTT_MAX_DEVICES) return nullptr;
+    shift %= gl::P;
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    PlanCache& pc = g_plan_cache[dev];
+    const auto key = std::make_tuple(lg_d, r, inverse, shift);
+    auto it = pc.index.find(key);
+    if (it != pc.index.end()) {
+        pc.lru.splice(pc.lru.begin(), pc.lru, it->second);
+        NttPlan* p = it->second->second;
+        // a plan filled on another stream (pcs_init re-bound the engine's stream): order this stream behind the fill
+        if (p->built_on != st && p->ready) cudaStreamWaitEvent(st, p->ready, 0);
+        return p;
+    }
     unsigned lg_n = lg_d + r;
     // primitive_root_of_unity(lg_n) = POWER_OF_TWO_GENERATOR^(2^(32-lg_n))   types.rs:268-272
     uint64_t root = h_pow(1753635133440165772ULL, 1ULL << (32 - lg_n));
@@ -118,38 +150,57 @@ NttPlan* ntt_plan_get(unsigned lg_d, unsigned r, bool inverse, uint64_t shift, c
     p->lg_d = lg_d;
     p->r = r;
     p->inverse = inverse;
-    p->shift = shift % gl::P;
+    p->shift = shift;
     p->scale = inverse ? gl::P - ((gl::P - 1) >> lg_d) : 1;  // inverse_2exp, types.rs:227-262
+    p->device = dev;
+    p->built_on = st;
     unsigned s0 = 0;
     for (unsigned nb : split_stages(lg_d)) {
         NttPass ps;
         ps.s0 = s0;
         ps.nb = nb;
         ps.L = lg_d - s0 - nb;
+        ps.gamma = ps.psi = nullptr;
         unsigned gbits = r + s0;
-        if (cudaMalloc(&ps.gamma, sizeof(uint64_t) << gbits) != cudaSuccess) return nullptr;
-        if (cudaMalloc(&ps.psi, sizeof(uint64_t) << (nb - 1)) != cudaSuccess) return nullptr;
+        // plain cudaMalloc (tables outlive any stream); a failure part-way frees what this plan already holds
+        bool ok = cudaMalloc(&ps.gamma, sizeof(uint64_t) << gbits) == cudaSuccess;
+        ok = ok && cudaMalloc(&ps.psi, sizeof(uint64_t) << (nb - 1)) == cudaSuccess;
+        p->passes.push_back(ps);
+        if (!ok) {
+            cudaGetLastError();
+            delete p;
+            return nullptr;
+        }
         size_t ng = (size_t)1 << gbits;
         k_fill_gamma<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(ps.gamma, gbits, root, p->shift, ps.L);
         uint64_t root_2nb = h_pow(root, 1ULL << (lg_n - nb));
         size_t nq = (size_t)1 << (nb - 1);
         k_fill_psi<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(ps.psi, nb, root_2nb);
-        p->passes.push_back(ps);
         s0 += nb;
     }
-    g_plans[key] = p;
+    if (cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(p->ready, st);
+    pc.lru.emplace_front(key, p);
+    pc.index[key] = pc.lru.begin();
+    while (pc.lru.size() > NTT_MAX_PLANS) {
+        // evict the least recently used plan; kernels already enqueued may still read its tables, and cudaFree only
+        // returns once the device is idle, so the tables outlive them
+        auto& victim = pc.lru.back();
+        pc.index.erase(victim.first);
+        delete victim.second;
+        pc.lru.pop_back();
+    }
     return p;
 }
 
+// frees the CURRENT device's plans (pcs_shutdown walks the contexts)
 void ntt_plans_free() {
-    for (auto& kv : g_plans) {
-        for (auto& ps : kv.second->passes) {
-            cudaFree(ps.gamma);
-            cudaFree(ps.psi);
-        }
-        delete kv.second;
-    }
-    g_plans.clear();
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= NTT_MAX_DEVICES) return;
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    PlanCache& pc = g_plan_cache[dev];
+    for (auto& kv : pc.lru) delete kv.second;
+    pc.lru.clear();
+    pc.index.clear();
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -202,7 +253,7 @@ __device__ __forceinline__ void run_stages(uint64_t (&x)[32], const uint64_t* tw
         uint64_t y[32];
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-            uint64_t t = gl::canon(gl::mul(x[j + 16], twp[j * STRIDE]));
+            uint64_t t = gl::canon(gl::mul_mad(x[j + 16], twp[j * STRIDE]));   // ALU-pipe bound: multiply-add reduction
             y[2 * j] = gl::add_lc(x[j], t);
             y[2 * j + 1] = gl::sub_lc(x[j], t);
         }
@@ -367,13 +418,14 @@ constexpr int lcl_max(int k1, int k2) { return (13 - k1 - k2) < (8 - k1) ? (13 -
 template <int K1, int K2, int LCL>
 static cudaError_t launch_pass(const PassArgs& a, unsigned grid, cudaStream_t st) {
     constexpr size_t smem = ((size_t)(1u << NTT_TILE_LOG) + 16 * K1 + 512 * K2 + 16) * sizeof(uint64_t);
-    static int attr_dev = -1;   // the opt-in to > 48 KB of dynamic shared memory is per device
-    int dev = -1;
+    static bool attr_set[NTT_MAX_DEVICES] = {false};   // the opt-in to > 48 KB of dynamic shared memory is per device
+    int dev = 0;
     cudaGetDevice(&dev);
-    if (attr_dev != dev) {
+    if (dev < 0 || dev >= NTT_MAX_DEVICES) return cudaErrorInvalidDevice;
+    if (!attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_ntt_pass<K1, K2, LCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_dev = dev;
+        attr_set[dev] = true;
     }
     k_ntt_pass<K1, K2, LCL><<<grid, NTT_THREADS, smem, st>>>(a);
     return cudaGetLastError();
@@ -489,6 +541,23 @@ __global__ void k_bitrev_permute(const uint64_t* __restrict__ in, size_t in_stri
     uint64_t v = in[j * in_stride + i];
     if (scale != 1) v = gl::canon(gl::mul(v, scale));
     out[j * out_stride + bi] = v;
+}
+
+// out[i] = canon(in[brev_{lg_n}(first + i)]) for i < count: the leaf-order slice [first, first + count) of a column given
+// in natural LDE order (salt columns of a shard, oracle.rs:119-123 + :84)
+__global__ void k_bitrev_gather(const uint64_t* __restrict__ in, unsigned lg_n, size_t first, size_t count,
+                                uint64_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    size_t src = lg_n ? (size_t)(__brevll((unsigned long long)(first + i)) >> (64 - lg_n)) : 0;
+    out[i] = gl::canon(in[src]);
+}
+
+cudaError_t launch_bitrev_gather(const uint64_t* in, unsigned lg_n, size_t first, size_t count, uint64_t* out,
+                                 cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    k_bitrev_gather<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(in, lg_n, first, count, out);
+    return cudaGetLastError();
 }
 
 uint64_t ntt_plan_scale(const NttPlan* plan) { return plan->scale; }

@@ -162,7 +162,7 @@ class CudaShardEngine:
     def shard_begin(self, plan, rank):
         h = C.c_void_p()
         self._order_after_torch()
-        _ffi.check(_ffi.lib().pcs_shard_begin(plan.w, plan.lg_d, plan.rate_bits, plan.coset_first(rank), plan.lg_cosets,
+        _ffi.check(_ffi.lib().pcs_shard_begin(plan.w, 0, plan.lg_d, plan.rate_bits, plan.coset_first(rank), plan.lg_cosets,
                                               plan.local_cap_height, C.byref(h)))
         return h
 

@@ -196,3 +196,24 @@ def test_streaming_kernels_use_tma_bulk_copies(built_lib):
         body = body[: body.index("Function :", 10)] if "Function :" in body[10:] else body
         assert "UBLKCP" in body, kernel
         assert "SYNCS" in body, kernel
+
+
+def test_c_abi_smoke_links_with_gcc_and_fails_loudly_without_a_gpu(tmp_path):
+    """tests/c_abi_smoke.c is plain C: it must compile and link against libpcs.so with gcc (no nvcc, no Python), and on a
+    box without a GPU the very first call fails with the engine's "no CPU fallback" message instead of computing anything."""
+    import subprocess
+
+    from test_gpu_multi import build_c_smoke
+
+    exe = build_c_smoke(tmp_path)
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present: the gpu-marked test runs the binary")
+    r = subprocess.run([exe, "1", "4"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 2
+    assert "no CPU fallback" in r.stderr

@@ -273,7 +273,7 @@ def test_cuda_streaming_shard_commit(w, lg_d, r, cap, world, groups):
     caps = []
     for k in range(world):
         h = C.c_void_p()
-        _ffi.check(L.pcs_shard_begin(w, lg_d, r, plan.coset_first(k), plan.lg_cosets, plan.local_cap_height, C.byref(h)))
+        _ffi.check(L.pcs_shard_begin(w, 0, lg_d, r, plan.coset_first(k), plan.lg_cosets, plan.local_cap_height, C.byref(h)))
         first = 0
         for gi, cnt in enumerate(groups):
             if gi % 2 == 0:
