@@ -86,7 +86,7 @@ BatchScope::BatchScope(const pcs_batch* b) : prev(g_cur) {
 BatchScope::~BatchScope() { ctx_enter((Ctx*)prev); }
 
 pcs_batch* batch_new() {
-    pcs_batch* b = batch_new();
+    pcs_batch* b = new pcs_batch();
     b->ctx = g_cur;
     return b;
 }

@@ -30,12 +30,14 @@ k_hash_cols(const uint64_t* __restrict__ cols, size_t col_stride, uint32_t width
         for (uint32_t j = 0; j < width; j += 8) {
             // a short last chunk overwrites only the first (width - j) lanes (hashing.rs:128-131)
 #pragma unroll
+            // no canonicalisation on the way in or between permutations: the permutation takes loose values (any u64
+            // congruent to the element) and the sponge state never leaves the registers; only the digest is canonical
             for (int k = 0; k < 8; k++)
-                if (j + k < width) s[k] = gl::canon(__ldg(p + (size_t)(j + k) * col_stride));
-            poseidon12(s);
+                if (j + k < width) s[k] = __ldg(p + (size_t)(j + k) * col_stride);
+            poseidon12<false>(s);
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) d[k] = s[k];
+        for (int k = 0; k < 4; k++) d[k] = gl::canon(s[k]);
     }
     uint64_t* slot = tree_mode ? digest_slot(digests, cap, lg_sub, 0, i) : digests + 4 * i;
     ulonglong2* o = reinterpret_cast<ulonglong2*>(slot);

@@ -29,13 +29,13 @@ k_compress(uint64_t* __restrict__ a, uint64_t* __restrict__ b, uint64_t* __restr
     }
     uint64_t s[12];
     ulonglong2 v0 = l[0], v1 = l[1], v2 = r[0], v3 = r[1];
-    s[0] = gl::canon(v0.x); s[1] = gl::canon(v0.y); s[2] = gl::canon(v1.x); s[3] = gl::canon(v1.y);
-    s[4] = gl::canon(v2.x); s[5] = gl::canon(v2.y); s[6] = gl::canon(v3.x); s[7] = gl::canon(v3.y);
+    s[0] = v0.x; s[1] = v0.y; s[2] = v1.x; s[3] = v1.y;   // loose inputs are fine: only the digest is canonicalised
+    s[4] = v2.x; s[5] = v2.y; s[6] = v3.x; s[7] = v3.y;
     s[8] = s[9] = s[10] = s[11] = 0;
-    poseidon12(s);
+    poseidon12<false>(s);
     ulonglong2* o = reinterpret_cast<ulonglong2*>(out);
-    o[0] = make_ulonglong2(s[0], s[1]);
-    o[1] = make_ulonglong2(s[2], s[3]);
+    o[0] = make_ulonglong2(gl::canon(s[0]), gl::canon(s[1]));
+    o[1] = make_ulonglong2(gl::canon(s[2]), gl::canon(s[3]));
 }
 
 // MerkleTree::prove: one thread per layer copies the sibling digest.

@@ -297,7 +297,8 @@ __device__ __forceinline__ void partial_round_d(uint64_t& x0, double (&dl)[12], 
 #define PCS_PARTIAL_FP64 1
 #endif
 
-// The permutation.  Input lanes: any u64 (loose); output lanes: canonical.
+// The permutation.  Input lanes: any u64 (loose); output lanes: canonical (CANON_OUT) or loose -- a sponge feeds the state
+// straight into the next permutation and canonicalises only the digest it finally emits.
 //
 // ONE round loop for all 30 rounds (the body is ~22 KB of SASS and must stay resident in the SM's
 // instruction cache: with separate full/partial loop bodies the kernel was instruction-fetch bound,
@@ -331,6 +332,7 @@ __device__ __forceinline__ void full_round(uint64_t (&s)[12], int r) {
 #endif
 }
 
+template <bool CANON_OUT = true>
 __device__ __forceinline__ void poseidon12(uint64_t (&s)[12]) {
     using namespace pconst;
 #pragma unroll
@@ -387,8 +389,10 @@ __device__ __forceinline__ void poseidon12(uint64_t (&s)[12]) {
 #endif
     }
 #endif
+    if (CANON_OUT) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl::canon(s[i]);
+        for (int i = 0; i < 12; i++) s[i] = gl::canon(s[i]);
+    }
 }
 
 }  // namespace pcs

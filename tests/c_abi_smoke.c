@@ -115,7 +115,7 @@ int main(int argc, char** argv) {
     int ok_rows = 1, ok_paths = 1;
     for (int k = 0; k < Q; k++) {
         ok_rows &= memcmp(rows + (size_t)k * w, ref_leaves + idx[k] * w, w * 8) == 0;
-        if (ref_merkle_prove(ref_dig, n, cap_height, idx[k], ref_sib)) return 3;
+        if (ref_merkle_prove(ref_dig, n, cap_height, idx[k], ref_sib) != (int)n_sib) return 3;
         ok_paths &= memcmp(sib + (size_t)k * n_sib * 4, ref_sib, (size_t)n_sib * 32) == 0;
     }
     /* polynomials[i] are kept (OpeningSet::new needs them, plonk/proof.rs:316-321) */
@@ -159,7 +159,7 @@ int main(int argc, char** argv) {
         for (int k = 0; k < Q; k++) {
             ok_multi &= memcmp(rows + (size_t)k * w, ref_leaves + idx[k] * w, w * 8) == 0;
             CHECK(pcs_multi_batch_prove(mb, idx[k], sib));
-            if (ref_merkle_prove(ref_dig, n, cap_height, idx[k], ref_sib)) return 3;
+            if (ref_merkle_prove(ref_dig, n, cap_height, idx[k], ref_sib) != (int)n_sib) return 3;
             ok_multi &= memcmp(sib, ref_sib, (size_t)n_sib * 32) == 0;
         }
         pcs_multi_batch_free(mb);

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle
-from helpers import P, brev, field_grid, seeded_polys
+from helpers import P, brev, canon, field_grid, seeded_polys
 
 pytestmark = pytest.mark.gpu
 
@@ -125,7 +125,7 @@ def test_shard_with_salt_rows(pcs, w, lg_d, r, cap_h, n_shards):
         _ffi.check(L.pcs_shard_finish(h, _ffi.ptr(cap)))
         rows = np.empty((hi - lo, w + 4), dtype=np.uint64)
         _ffi.check(L.pcs_batch_leaves(h, 0, hi - lo, _ffi.ptr(rows)))
-        assert np.array_equal(rows, ref["leaves"][lo:hi])
+        assert np.array_equal(rows, canon(ref["leaves"][lo:hi]))     # the oracle keeps the salts as given, the engine emits canonical values
         caps.append(cap)
         L.pcs_batch_free(h)
     from plonky2_demo_b200.hashing import PoseidonHash
