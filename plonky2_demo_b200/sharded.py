@@ -9,6 +9,16 @@ identity of the LDE (oracle.rs:83-84): after the row bit-reversal, le
     hence whole cap subtrees and a contiguous slice of the reference's `digests` (merkle_tree.rs:43-46);
   * it needs every polynomial's d coefficients (W*d elements), never another rank's LDE output.
 
+Two partitions are built (SURVEY 8e lists both; results are bit-identical):
+  "coset"    (default when world <= 2^rate_bits): described above -- the coefficients travel (all-gather, or peer loads
+             fused into the first NTT pass), every rank extends its own cosets;
+  "alltoall" (the north-star's split; any power-of-two world up to the number of leaves, blinding included): the
+             polynomials are partitioned, every rank extends ITS polynomials over all cosets, and one NCCL all-to-all over
+             NVLink carries the LDE rows to the rank that owns their leaf range (rows land directly in that rank's leaf
+             buffer, poly-major, ready for hashing).  Leaf ranges need not be whole cosets, so world may exceed 2^rate_bits.
+Bytes received per rank: coset = (G-1)/G * W*d*8, alltoall = (G-1)/G * W*N*8/G -- equal at G = 2^rate_bits, the coset
+partition is cheaper below it.
+
 Exchange steps (the only collectives on the path):
   1. all-gather of the coefficients when the input is polynomial-partitioned (rank r holds a block of the
      W polynomials, e.g. after a per-rank IFFT in from_values): W*d*8 bytes in total, 8x less than the
@@ -45,13 +55,17 @@ class ShardPlan:
         if world < 1 or world & (world - 1):
             raise ValueError(f"world size must be a power of two, got {world}")
         lg_w = log2_strict(world)
-        if lg_w > rate_bits:
-            raise ValueError(f"cannot shard 2^{rate_bits} coset blocks over {world} ranks (need world <= 2^rate_bits)")
+        if lg_w > lg_d + rate_bits:
+            raise ValueError(f"cannot shard {1 << (lg_d + rate_bits)} leaves over {world} ranks")
         if cap_height > lg_d + rate_bits:
             raise ValueError(f"cap_height={cap_height} should be at most log2(leaves.len())={lg_d + rate_bits}")
         self.w, self.lg_d, self.rate_bits, self.cap_height, self.world = w, lg_d, rate_bits, cap_height, world
         self.lg_world = lg_w
-        self.lg_cosets = rate_bits - lg_w                     # coset blocks per rank (log2)
+        # whole coset blocks per rank: the coefficient exchange ("coset" partition) needs it; the all-to-all of LDE rows
+        # works for any power-of-two world
+        self.coset_partition = lg_w <= rate_bits
+        self.lg_cosets = rate_bits - lg_w                     # coset blocks per rank (log2; negative: a fraction of a block)
+        self.lg_local = lg_d + rate_bits - lg_w               # log2(leaves per rank)
         self.local_cap_height = max(cap_height - lg_w, 0)
         self.top_levels = max(lg_w - cap_height, 0)           # levels combined from the ranks' roots
         self.n_leaves = 1 << (lg_d + rate_bits)
@@ -63,6 +77,9 @@ class ShardPlan:
         self.w_chunk = -(-w // self.chunks)
 
     def coset_first(self, rank):
+        if not self.coset_partition:
+            raise ValueError(f"cannot shard 2^{self.rate_bits} coset blocks over {self.world} ranks (need world <= 2^rate_bits); "
+                             "use exchange='alltoall'")
         return rank << self.lg_cosets
 
     def leaf_range(self, rank):
@@ -120,8 +137,46 @@ class ShardPlan:
         return np.concatenate(sib, axis=0)
 
 
+def reverse_bits_array(idx, bits):
+    """vectorised reverse_bits (plonky2/src/util/mod.rs:30-38) of a uint64 numpy array"""
+    idx = np.asarray(idx, dtype=np.uint64)
+    out = np.zeros_like(idx)
+    for b in range(bits):
+        out |= ((idx >> np.uint64(b)) & np.uint64(1)) << np.uint64(bits - 1 - b)
+    return out
+
+
+def salt_leaf_slice(salts, lg_n, first, count):
+    """salts: [salt_w][N] in natural LDE order (oracle.rs:119-123) -> rows [first, first+count) in LEAF order
+    (reverse_index_bits_in_place, oracle.rs:84)."""
+    src = reverse_bits_array(np.arange(first, first + count, dtype=np.uint64), lg_n).astype(np.int64)
+    return np.ascontiguousarray(np.asarray(salts, dtype=np.uint64)[:, src])
+
+
+class _DeviceView:
+    """__cuda_array_interface__ over raw device memory owned by the engine (a shard's LDE rows)"""
+
+    def __init__(self, ptr, n_elems):
+        self.__cuda_array_interface__ = {"shape": (int(n_elems),), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+
 class CudaShardEngine:
     """Per-rank compute through the C ABI (no CPU path)."""
+
+    def __init__(self):
+        # the engine's current context must be this rank's GPU: a rank that forgot pcs.init(local_rank) would otherwise
+        # run on device 0 with another GPU's pointers
+        try:
+            import torch
+            if torch.cuda.is_available():
+                L = _ffi.lib()
+                if L.pcs_device() < 0:
+                    _ffi.check(L.pcs_init(torch.cuda.current_device(), None))
+                if L.pcs_device() != torch.cuda.current_device():
+                    raise RuntimeError(f"the engine is bound to GPU {L.pcs_device()} but torch's current device is "
+                                       f"{torch.cuda.current_device()}: call plonky2_demo_b200.init(local_rank[, stream]) first")
+        except ImportError:
+            pass
 
     @staticmethod
     def _order_after_torch():
@@ -159,12 +214,59 @@ class CudaShardEngine:
                                                   plan.local_cap_height, None, 0, _ffi.PCS_DEVICE_PTRS, _ffi.ptr(cap), C.byref(h)))
         return h, cap
 
-    def shard_begin(self, plan, rank):
+    def shard_begin(self, plan, rank, salt_w=0):
         h = C.c_void_p()
         self._order_after_torch()
-        _ffi.check(_ffi.lib().pcs_shard_begin(plan.w, 0, plan.lg_d, plan.rate_bits, plan.coset_first(rank), plan.lg_cosets,
+        _ffi.check(_ffi.lib().pcs_shard_begin(plan.w, salt_w, plan.lg_d, plan.rate_bits, plan.coset_first(rank), plan.lg_cosets,
                                               plan.local_cap_height, C.byref(h)))
         return h
+
+    # ---- the all-to-all partition: LDE rows computed by the ranks that hold the polynomials ----
+    def lde_full(self, coeffs, rate_bits):
+        """coeffs: torch CUDA int64 [w_loc][d] -> [w_loc][N] in leaf order (pcs_coset_lde_dev, all cosets)"""
+        import torch
+
+        w_loc, d = int(coeffs.shape[0]), int(coeffs.shape[1])
+        out = torch.empty((w_loc, d << rate_bits), dtype=torch.int64, device=coeffs.device)
+        if w_loc:
+            self._order_after_torch()
+            _ffi.check(_ffi.lib().pcs_coset_lde_dev(_ffi.dev_ptr_array(coeffs.data_ptr(), w_loc, d), w_loc, log2_strict(d), rate_bits, 7,
+                                                    C.c_void_p(out.data_ptr())))
+            self._order_torch_after_engine()
+        return out
+
+    @staticmethod
+    def _order_torch_after_engine():
+        import torch
+
+        if _ffi.lib().pcs_stream() != torch.cuda.current_stream().cuda_stream:
+            _ffi.check(_ffi.lib().pcs_synchronize())
+
+    def rows_begin(self, width, salt_w, lg_n_local, local_cap_height):
+        h = C.c_void_p()
+        self._order_after_torch()
+        _ffi.check(_ffi.lib().pcs_shard_begin_rows(width, salt_w, lg_n_local, local_cap_height, C.byref(h)))
+        self._order_torch_after_engine()      # the buffer exists before torch / NCCL write into it
+        return h
+
+    def rows_buffer(self, handle, rows, n_local):
+        """torch view [rows][n_local] of the shard's first `rows` LDE rows (written in place by the all-to-all)"""
+        import torch
+
+        base = _ffi.lib().pcs_batch_lde_dev(handle)
+        return torch.as_tensor(_DeviceView(base, rows * n_local), device="cuda").view(rows, n_local)
+
+    def set_rows(self, handle, row_first, rows, canonical):
+        """rows: torch CUDA int64 [count][n_local], leaf order"""
+        self._order_after_torch()
+        count, n_local = int(rows.shape[0]), int(rows.shape[1])
+        _ffi.check(_ffi.lib().pcs_shard_set_rows(handle, row_first, count, _ffi.dev_ptr_array(rows.data_ptr(), count, n_local),
+                                                 1 if canonical else 0))
+
+    def to_device(self, host_rows, like):
+        import torch
+
+        return torch.from_numpy(np.ascontiguousarray(host_rows).view(np.int64)).to(like.device)
 
     def shard_extend(self, handle, poly_first, coeffs, count):
         """coeffs: torch CUDA int64 tensor [>= count][d] holding polynomials poly_first .. poly_first+count-1"""
@@ -174,6 +276,7 @@ class CudaShardEngine:
 
     def shard_finish(self, handle, plan):
         cap = np.empty((plan.local_cap_len(), 4), dtype=np.uint64)
+        self._order_after_torch()
         _ffi.check(_ffi.lib().pcs_shard_finish(handle, _ffi.ptr(cap)))
         return cap
 
@@ -245,7 +348,7 @@ class ShardedPolynomialBatch:
     # ---- constructors (collective: every rank of `group` calls them) ---------------------------------
     @classmethod
     def from_coeffs(cls, local_coeffs, n_polys, rate_bits, cap_height, group=None, engine=None, partitioned=True,
-                    exchange="auto", chunks=1):
+                    exchange="auto", chunks=1, blinding=False, salts=None, gather_coeffs=False):
         """oracle.rs:68-98 over a process group.
 
         partitioned=True : `local_coeffs` is this rank's block [poly_range(rank)][d] of the n_polys polynomials
@@ -255,15 +358,24 @@ class ShardedPolynomialBatch:
                            groups, each block-distributed over the ranks (ShardPlan.poly_ranges); `local_coeffs`
                            holds this rank's rows in chunk order and may live in PINNED HOST memory.  Chunk c+1 is
                            copied / all-gathered on a side stream while the LDE of chunk c runs.
-        exchange         : how the other ranks' coefficient blocks reach this rank's LDE --
-            "allgather": NCCL all-gather into a local [W][d] matrix, then the LDE;
-            "peer"     : NO collective: every block sits in symmetric memory and the first NTT pass of each rank
-                         loads the other ranks' coefficients straight from their HBM over NVLink (fused exchange +
+        exchange         : how the data a rank hashes reaches it --
+            "allgather": coset partition; NCCL all-gather of the coefficients into a local [W][d] matrix, then the LDE;
+            "peer"     : coset partition; NO collective: every block sits in symmetric memory and the first NTT pass of each
+                         rank loads the other ranks' coefficients straight from their HBM over NVLink (fused exchange +
                          compute, transfer hidden behind the butterflies);
-            "auto"     : "allgather".  Measured on 8 x B200 (135 x 2^20, one coset per rank, profiles/r01_scaling_v5.md):
-                         the peer-reading LDE costs 3.41 ms against 2.72 ms + ~1.4 ms of all-gather, but the two
-                         cross-rank barriers and the symmetric-buffer copy it needs cost more than that on the
-                         host side (21.9 ms vs 18.3 ms per commitment), so the collective stays the default.
+            "alltoall" : polynomial partition (the north-star's split): every rank extends its own polynomials over all
+                         cosets and ONE NCCL all-to-all carries the LDE rows to the rank that hashes their leaf range.
+                         Works for any power-of-two world (also > 2^rate_bits) and needs partitioned=True, chunks=1;
+            "auto"     : "allgather" when world <= 2^rate_bits, else "alltoall".  Measured on 8 x B200 (135 x 2^20, one coset
+                         per rank, profiles/r01_scaling_v5.md): the peer-reading LDE costs 3.41 ms against 2.72 ms + ~1.4 ms
+                         of all-gather, but the two cross-rank barriers and the symmetric-buffer copy it needs cost more
+                         than that on the host side across PROCESSES (21.9 ms vs 18.3 ms per commitment), so the
+                         collective stays the default here; inside one process (pcs_multi_*) the peer form is the default.
+        blinding / salts : SALT_SIZE = 4 extra leaf columns (oracle.rs:26,119-123).  `salts` = [4][N] in natural LDE order,
+                           the same array on every rank (reproducible commitments; a rank uses only its leaf range); with
+                           blinding=True and salts=None every rank draws the salt values of its own leaves from the OS.
+        gather_coeffs    : "alltoall" only: also all-gather the coefficients so that every rank can serve the opening
+                           proof (poly_device_ptrs); the coset partition replicates them anyway.
         """
         import torch
         import torch.distributed as dist
@@ -274,9 +386,34 @@ class ShardedPolynomialBatch:
         d = int(local_coeffs.shape[1])
         plan = ShardPlan(n_polys, log2_strict(d), rate_bits, cap_height, world, chunks if (partitioned and world > 1) else 1)
         if exchange == "auto":
-            exchange = "allgather"
+            exchange = "allgather" if plan.coset_partition else "alltoall"
+        if exchange not in ("allgather", "peer", "alltoall"):
+            raise ValueError(f"unknown exchange {exchange!r}")
+        # ---- blinding: this rank's slice [4][local_leaves] of the salt columns, in leaf order ----
+        salt_rows = None
+        if salts is not None or blinding:
+            lo_leaf, hi_leaf = plan.leaf_range(rank)
+            if salts is not None:
+                sal = np.asarray(salts, dtype=np.uint64)
+                if sal.shape != (4, plan.n_leaves):
+                    raise ValueError(f"salts must be [4][{plan.n_leaves}] (SALT_SIZE columns of N values, oracle.rs:26), got {sal.shape}")
+                salt_rows = salt_leaf_slice(sal, plan.lg_d + rate_bits, lo_leaf, hi_leaf - lo_leaf)
+            else:
+                # F::rand_vec (types.rs:33-35, OsRng): every rank draws the values of its own leaves
+                rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(16), "little"))
+                salt_rows = rng.integers(0, 0xFFFFFFFF00000001, size=(4, hi_leaf - lo_leaf), dtype=np.uint64)
+        if exchange == "alltoall" and world > 1:
+            if not partitioned or plan.chunks > 1:
+                raise ValueError("exchange='alltoall' needs partitioned=True and chunks=1")
+            return cls._from_coeffs_alltoall(local_coeffs, plan, rank, world, group, engine, salt_rows, gather_coeffs)
+        if not plan.coset_partition:
+            plan.coset_first(rank)    # raises: the coset partition needs world <= 2^rate_bits
         if plan.chunks > 1:
-            return cls._from_coeffs_streaming(local_coeffs, plan, rank, world, group, engine)
+            return cls._from_coeffs_streaming(local_coeffs, plan, rank, world, group, engine, salt_rows)
+        if salt_rows is not None:
+            # one-shot coset partition with salts: go through begin / extend / set_rows / finish
+            return cls._from_coeffs_streaming(local_coeffs, plan, rank, world, group, engine, salt_rows, one_shot_exchange=exchange,
+                                              partitioned=partitioned)
         poly_ptrs = None
         if partitioned and world > 1 and exchange == "peer":
             lo, hi = plan.poly_range(rank)
@@ -308,7 +445,7 @@ class ShardedPolynomialBatch:
         self = cls()
         self.plan, self.rank, self.world, self.group, self.engine = plan, rank, world, group, engine
         self.degree_log, self.rate_bits, self.blinding, self.cap_height = plan.lg_d, rate_bits, False, cap_height
-        self.n_polys = n_polys
+        self.n_polys, self.salt_w = n_polys, 0
         self._coeffs = full          # PolynomialBatch.polynomials (replicated; only the local block with exchange="peer")
         if poly_ptrs is not None:
             self._h, local_cap = engine.commit_shard(None, n_polys, plan, rank, poly_ptrs=poly_ptrs)
@@ -329,7 +466,8 @@ class ShardedPolynomialBatch:
         return self
 
     @classmethod
-    def _from_coeffs_streaming(cls, local_coeffs, plan, rank, world, group, engine):
+    def _from_coeffs_streaming(cls, local_coeffs, plan, rank, world, group, engine, salt_rows=None, one_shot_exchange=None,
+                               partitioned=True):
         """chunked exchange overlapped with the LDE: side stream = (H2D of chunk c) -> all-gather of chunk c;
         main stream = LDE of chunk c as soon as its gather has landed; then leaf hashing and the subtrees."""
         import torch
@@ -337,6 +475,20 @@ class ShardedPolynomialBatch:
 
         d = int(local_coeffs.shape[1])
         ranges = plan.poly_ranges(rank)
+        if not partitioned or world == 1:
+            # every rank holds all coefficients already: one group, nothing to gather
+            self = cls()
+            self.plan, self.rank, self.world, self.group, self.engine = plan, rank, world, group, engine
+            self.degree_log, self.rate_bits, self.blinding, self.cap_height = plan.lg_d, plan.rate_bits, salt_rows is not None, plan.cap_height
+            self.n_polys, self.salt_w = plan.w, 0 if salt_rows is None else 4
+            full = local_coeffs.contiguous()
+            self._h = engine.shard_begin(plan, rank, self.salt_w)
+            engine.shard_extend(self._h, 0, full, plan.w)
+            if salt_rows is not None:
+                engine.set_rows(self._h, plan.w, engine.to_device(salt_rows, full), False)
+            local_cap = engine.shard_finish(self._h, plan)
+            self._coeffs = full
+            return cls._finish_caps(self, local_cap, full.device, world, group, engine, "none")
         if local_coeffs.shape[0] != sum(hi - lo for lo, hi in ranges):
             raise ValueError(f"rank {rank} must hold polynomials {ranges} ({sum(hi - lo for lo, hi in ranges)} rows), "
                              f"got {local_coeffs.shape[0]}")
@@ -369,25 +521,82 @@ class ShardedPolynomialBatch:
             events.append(ev)
         self = cls()
         self.plan, self.rank, self.world, self.group, self.engine = plan, rank, world, group, engine
-        self.degree_log, self.rate_bits, self.blinding, self.cap_height = plan.lg_d, plan.rate_bits, False, plan.cap_height
-        self.n_polys = plan.w
-        self._h = engine.shard_begin(plan, rank)
+        self.degree_log, self.rate_bits, self.blinding, self.cap_height = plan.lg_d, plan.rate_bits, salt_rows is not None, plan.cap_height
+        self.n_polys, self.salt_w = plan.w, 0 if salt_rows is None else 4
+        self._h = engine.shard_begin(plan, rank, self.salt_w)
         for c in range(plan.chunks):
             clo, chi = plan.chunk_range(c)
             if cuda:
                 main.wait_event(events[c])
             engine.shard_extend(self._h, clo, gathered[c][0], chi - clo)
+        if salt_rows is not None:
+            engine.set_rows(self._h, plan.w, engine.to_device(salt_rows, gathered[0][0]), False)
         local_cap = engine.shard_finish(self._h, plan)
         self._coeffs = gathered          # keeps the gathered chunks alive ([chunk][world*m][d]); polynomials of chunk c = rows [0, len_c)
-        mine = torch.from_numpy(local_cap.view(np.int64)).to(dev)
-        allc = torch.empty((world * mine.shape[0], 4), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allc, mine, group=group)
-        caps = allc.cpu().numpy().view(np.uint64).reshape(world, -1, 4)
-        self._local_caps = caps
-        self.cap = plan.assemble_cap(caps, engine.two_to_one)
-        self.exchange = f"allgather, {plan.chunks} chunks overlapped with the LDE"
         self._dev = dev
+        return cls._finish_caps(self, local_cap, dev, world, group, engine,
+                                f"allgather, {plan.chunks} chunk{'s' if plan.chunks > 1 else ''} overlapped with the LDE")
+
+    @staticmethod
+    def _finish_caps(self, local_cap, dev, world, group, engine, exchange):
+        """exchange step 2: all-gather of the local caps, top levels on every rank"""
+        import torch
+        import torch.distributed as dist
+
+        if world > 1:
+            mine = torch.from_numpy(local_cap.view(np.int64)).to(dev)
+            allc = torch.empty((world * mine.shape[0], 4), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allc, mine, group=group)
+            caps = allc.cpu().numpy().view(np.uint64).reshape(world, -1, 4)
+        else:
+            caps = local_cap[None]
+        self._local_caps = caps
+        self.cap = self.plan.assemble_cap(caps, engine.two_to_one)
+        self.exchange = exchange
         return self
+
+    @classmethod
+    def _from_coeffs_alltoall(cls, local_coeffs, plan, rank, world, group, engine, salt_rows, gather_coeffs):
+        """The north-star's split: polynomial-partitioned LDE, then an all-to-all of LDE rows into leaf-range shards.
+        Rank r extends its block [poly_range(r)][d] over ALL cosets (leaf order), sends rows [w_r][q N/G : (q+1) N/G] to rank
+        q, and receives every polynomial's slice of its own leaf range straight into its shard's leaf buffer [W][N/G]
+        (poly-major: the layout the hash kernel reads).  Then leaf hashing, the local subtree(s), cap all-gather."""
+        import torch
+        import torch.distributed as dist
+
+        lo, hi = plan.poly_range(rank)
+        w_loc, n_loc = hi - lo, plan.local_leaves
+        if local_coeffs.shape[0] != w_loc:
+            raise ValueError(f"rank {rank} must hold polynomials [{lo}, {hi}), got {local_coeffs.shape[0]} rows")
+        dev = local_coeffs.device
+        self = cls()
+        self.plan, self.rank, self.world, self.group, self.engine = plan, rank, world, group, engine
+        self.degree_log, self.rate_bits, self.blinding, self.cap_height = plan.lg_d, plan.rate_bits, salt_rows is not None, plan.cap_height
+        self.n_polys, self.salt_w = plan.w, 0 if salt_rows is None else 4
+        lde = engine.lde_full(local_coeffs.contiguous(), plan.rate_bits)                       # [w_loc][N], leaf order
+        send = lde.view(w_loc, world, n_loc).permute(1, 0, 2).contiguous()                     # [dest][w_loc][n_loc]
+        del lde
+        self._h = engine.rows_begin(plan.w + self.salt_w, self.salt_w, plan.lg_local, plan.local_cap_height)
+        recv = engine.rows_buffer(self._h, plan.w, n_loc)                                      # the shard's own rows [W][n_loc]
+        in_splits = [w_loc * n_loc] * world
+        out_splits = [(plan.poly_range(q)[1] - plan.poly_range(q)[0]) * n_loc for q in range(world)]
+        dist.all_to_all_single(recv.view(-1), send.view(-1), out_splits, in_splits, group=group)
+        del send
+        if salt_rows is not None:
+            engine.set_rows(self._h, plan.w, engine.to_device(salt_rows, local_coeffs), False)
+        local_cap = engine.shard_finish(self._h, plan)
+        if gather_coeffs:
+            full = torch.empty((world * plan.w_max, 1 << plan.lg_d), dtype=torch.int64, device=dev)
+            mine = local_coeffs.contiguous()
+            if w_loc < plan.w_max:
+                mine = torch.zeros((plan.w_max, 1 << plan.lg_d), dtype=torch.int64, device=dev)
+                mine[:w_loc] = local_coeffs
+            dist.all_gather_into_tensor(full, mine, group=group)
+            self._coeffs = full
+        else:
+            self._coeffs = local_coeffs
+        self._dev = dev
+        return cls._finish_caps(self, local_cap, dev, world, group, engine, "alltoall of LDE rows (polynomial-partitioned LDE)")
 
     @classmethod
     def from_values(cls, local_values, n_polys, rate_bits, cap_height, group=None, engine=None):
@@ -418,9 +627,10 @@ class ShardedPolynomialBatch:
         idx = np.asarray(list(leaf_indices), dtype=np.int64)
         lo, hi = self.plan.leaf_range(self.rank)
         mine = (idx >= lo) & (idx < hi)
-        rows = np.zeros((idx.shape[0], self.n_polys), dtype=np.uint64)
+        width = self.n_polys + getattr(self, "salt_w", 0)
+        rows = np.zeros((idx.shape[0], width), dtype=np.uint64)
         if mine.any():
-            rows[mine] = self.engine.get_rows(self._h, idx[mine] - lo, self.n_polys)
+            rows[mine] = self.engine.get_rows(self._h, idx[mine] - lo, width)
         if self.world > 1:
             t = torch.from_numpy(rows.view(np.int64)).to(self._device())
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)   # disjoint owners: sum == select
@@ -430,7 +640,7 @@ class ShardedPolynomialBatch:
     def get_lde_values(self, index, step):
         """oracle.rs:128-133"""
         leaf = reverse_bits(index * step, self.degree_log + self.rate_bits)
-        return self.get_rows([leaf])[0]
+        return self.get_rows([leaf])[0][: self.n_polys]      # minus the salt columns (oracle.rs:131-132)
 
     def prove(self, leaf_index):
         """MerkleTree::prove (merkle_tree.rs:173-207) for a global leaf index (collective)."""

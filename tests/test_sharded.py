@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle
-from helpers import seeded_polys
+from helpers import P, seeded_polys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -36,9 +36,10 @@ class OracleShardEngine:
         self.batches[h] = (np.ascontiguousarray(leaves[lo:hi]), digests, plan)
         return h, cap
 
-    def shard_begin(self, plan, rank):
+    def shard_begin(self, plan, rank, salt_w=0):
         h = len(self.batches) + 1
-        self.batches[h] = {"plan": plan, "rank": rank, "coeffs": np.zeros((plan.w, 1 << plan.lg_d), dtype=np.uint64), "seen": 0}
+        self.batches[h] = {"plan": plan, "rank": rank, "coeffs": np.zeros((plan.w, 1 << plan.lg_d), dtype=np.uint64), "seen": 0,
+                           "salt_w": salt_w, "salts": None}
         return h
 
     def shard_extend(self, h, poly_first, coeffs, count):
@@ -46,13 +47,58 @@ class OracleShardEngine:
         b["coeffs"][poly_first : poly_first + count] = self._u64(coeffs)[:count]
         b["seen"] += count
 
+    # ---- rows shards (all-to-all partition) and salt rows ----
+    def lde_full(self, coeffs, rate_bits):
+        import torch
+
+        c = np.ascontiguousarray(self._u64(coeffs))
+        if c.shape[0] == 0:
+            return torch.empty((0, c.shape[1] << rate_bits), dtype=torch.int64)
+        leaves = oracle.transpose_bitrev(oracle.coset_lde(c, rate_bits))          # [N][w_loc], leaf order
+        return torch.from_numpy(np.ascontiguousarray(leaves.T).view(np.int64).copy())
+
+    def rows_begin(self, width, salt_w, lg_n_local, local_cap_height):
+        import torch
+
+        h = len(self.batches) + 1
+        self.batches[h] = {"rows": torch.zeros((width, 1 << lg_n_local), dtype=torch.int64), "lch": local_cap_height, "salt_w": salt_w}
+        return h
+
+    def rows_buffer(self, h, rows, n_local):
+        return self.batches[h]["rows"][:rows]
+
+    def set_rows(self, h, row_first, rows, canonical):
+        b = self.batches[h]
+        if "rows" in b:
+            b["rows"][row_first : row_first + rows.shape[0]] = rows
+        else:
+            assert row_first == b["plan"].w and rows.shape[0] == b["salt_w"]
+            b["salts"] = self._u64(rows).copy()
+
+    def to_device(self, host_rows, like):
+        import torch
+
+        return torch.from_numpy(np.ascontiguousarray(host_rows).view(np.int64).copy())
+
     def shard_finish(self, h, plan):
         import torch
 
         b = self.batches.pop(h)
+        if "rows" in b:
+            leaves = np.ascontiguousarray(self._u64(b["rows"]).T) % np.uint64(P)
+            digests, cap = oracle.merkle_build(leaves, b["lch"])
+            self.batches[h] = (leaves, digests, plan)
+            return cap
         assert b["seen"] == plan.w
-        h2, cap = self.commit_shard(torch.from_numpy(b["coeffs"].view(np.int64)), plan.w, plan, b["rank"])
-        self.batches[h] = self.batches.pop(h2)
+        c = b["coeffs"]
+        leaves = oracle.transpose_bitrev(oracle.coset_lde(c, plan.rate_bits))
+        lo, hi = plan.leaf_range(b["rank"])
+        leaves = np.ascontiguousarray(leaves[lo:hi])
+        if b["salt_w"]:
+            assert b["salts"] is not None
+            leaves = np.ascontiguousarray(np.concatenate([leaves, (b["salts"] % np.uint64(P)).T], axis=1))
+        digests, cap = oracle.merkle_build(leaves, plan.local_cap_height)
+        self.batches[h] = (leaves, digests, plan)
         return cap
 
     def two_to_one(self, l, r):
@@ -117,8 +163,12 @@ def test_shard_plan_rejects():
 
     with pytest.raises(ValueError, match="power of two"):
         ShardPlan(4, 4, 3, 0, 3)
+    p = ShardPlan(4, 4, 1, 0, 4)                      # more ranks than coset blocks: only the all-to-all partition applies
+    assert not p.coset_partition and p.local_leaves == 8 and p.lg_local == 3
     with pytest.raises(ValueError, match="world <= 2\\^rate_bits"):
-        ShardPlan(4, 4, 1, 0, 4)
+        p.coset_first(1)
+    with pytest.raises(ValueError, match="cannot shard 32 leaves over 64 ranks"):
+        ShardPlan(4, 4, 1, 0, 64)
     with pytest.raises(ValueError, match="cap_height=9 should be at most"):
         ShardPlan(4, 4, 3, 9, 2)
 
@@ -155,7 +205,7 @@ def test_single_process_shards_assemble_to_reference(w, lg_d, r, cap, world):
 # ---------------------------------------------------------------------------------------------
 # collectives under gloo, world_size 2
 # ---------------------------------------------------------------------------------------------
-def _gloo_worker(rank, world, port, w, lg_d, r, cap, from_values, q, chunks=1):
+def _gloo_worker(rank, world, port, w, lg_d, r, cap, from_values, q, chunks=1, exchange="auto", blind=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -168,7 +218,8 @@ def _gloo_worker(rank, world, port, w, lg_d, r, cap, from_values, q, chunks=1):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         coeffs = seeded_polys(w, 1 << lg_d, base_seed=5)
-        ref = oracle.commit_from_coeffs(coeffs, r, cap)
+        salts = seeded_polys(4, 1 << (lg_d + r), base_seed=0x5A1) if blind else None
+        ref = oracle.commit_from_coeffs(coeffs, r, cap, salts=salts)
         plan = ShardPlan(w, lg_d, r, cap, world, chunks)
         src = oracle.fft(coeffs) if from_values else coeffs
         local = torch.from_numpy(np.ascontiguousarray(src[plan.local_polys(rank)]).view(np.int64).copy())
@@ -176,13 +227,15 @@ def _gloo_worker(rank, world, port, w, lg_d, r, cap, from_values, q, chunks=1):
         if from_values:
             b = ShardedPolynomialBatch.from_values(local, w, r, cap, engine=eng)
         else:
-            b = ShardedPolynomialBatch.from_coeffs(local, w, r, cap, engine=eng, chunks=chunks)
+            b = ShardedPolynomialBatch.from_coeffs(local, w, r, cap, engine=eng, chunks=chunks, exchange=exchange, salts=salts)
         ok = np.array_equal(b.cap, ref["cap"])
-        if chunks == 1:
+        if b.exchange.startswith("alltoall") != (exchange == "alltoall" or not plan.coset_partition):
+            ok = False
+        if chunks == 1 and not b.exchange.startswith("alltoall") and not blind:
             ok &= np.array_equal(b._coeffs.numpy().view(np.uint64)[:w], coeffs)
         leaves = [0, plan.local_leaves - 1, plan.local_leaves, plan.n_leaves - 1]
         ok &= np.array_equal(b.get_rows(leaves), ref["leaves"][leaves])
-        ok &= np.array_equal(b.get_lde_values(3, 2), ref["leaves"][int(format(6, f"0{lg_d + r}b")[::-1], 2)])
+        ok &= np.array_equal(b.get_lde_values(3, 2), ref["leaves"][int(format(6, f"0{lg_d + r}b")[::-1], 2)][:w])
         for leaf in leaves:
             pr = b.prove(leaf)
             ok &= bool(oracle.merkle_verify(ref["leaves"][leaf], leaf, ref["cap"], pr.siblings))
@@ -192,7 +245,6 @@ def _gloo_worker(rank, world, port, w, lg_d, r, cap, from_values, q, chunks=1):
             ok &= np.array_equal(pr.siblings, b.prove(leaf).siblings)
             ok &= bool(oracle.merkle_verify(ref["leaves"][leaf], leaf, ref["cap"], pr.siblings))
         if plan.top_levels == 0:
-            l0, l1 = plan.leaf_range(rank)
             per = ref["digests"].shape[0] // world
             ok &= np.array_equal(b.local_digests(), ref["digests"][rank * per:(rank + 1) * per])
         q.put((rank, bool(ok)))
@@ -200,8 +252,15 @@ def _gloo_worker(rank, world, port, w, lg_d, r, cap, from_values, q, chunks=1):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("w,lg_d,r,cap,from_values,chunks", [(9, 5, 3, 4, False, 1), (7, 4, 1, 0, False, 1), (9, 5, 3, 4, True, 1), (9, 5, 3, 4, False, 3)])
-def test_gloo_world2_sharded_commit(w, lg_d, r, cap, from_values, chunks):
+@pytest.mark.parametrize("w,lg_d,r,cap,from_values,chunks,exchange,blind", [
+    (9, 5, 3, 4, False, 1, "auto", False), (7, 4, 1, 0, False, 1, "auto", False), (9, 5, 3, 4, True, 1, "auto", False),
+    (9, 5, 3, 4, False, 3, "auto", False),
+    (9, 5, 3, 4, False, 1, "alltoall", False),          # the north-star's split: all-to-all of LDE rows
+    (7, 4, 0, 0, False, 1, "auto", False),              # rate_bits 0: more ranks than coset blocks -> all-to-all, half a coset per rank
+    (5, 3, 1, 3, False, 1, "alltoall", True),           # blinding salts through the all-to-all partition (ragged polynomial blocks)
+    (9, 5, 3, 4, False, 1, "auto", True), (9, 5, 2, 1, False, 2, "auto", True),   # salts through the coset partition, one-shot and streaming
+])
+def test_gloo_world2_sharded_commit(w, lg_d, r, cap, from_values, chunks, exchange, blind):
     import socket
 
     import torch.multiprocessing as mp
@@ -212,7 +271,7 @@ def test_gloo_world2_sharded_commit(w, lg_d, r, cap, from_values, chunks):
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_gloo_worker, args=(k, 2, port, w, lg_d, r, cap, from_values, q, chunks)) for k in range(2)]
+    procs = [ctx.Process(target=_gloo_worker, args=(k, 2, port, w, lg_d, r, cap, from_values, q, chunks, exchange, blind)) for k in range(2)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in procs)
