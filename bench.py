@@ -76,6 +76,7 @@ def parse():
     ap.add_argument("--large-commit", default="auto", choices=["auto", "on", "off"],
                     help="N = 8: add BASELINE configs[4], one 135 x 2^24 commitment sharded over the box, with sampled-leaf parity")
     ap.add_argument("--no-from-values", action="store_true", help="skip the from_values timing at the headline size")
+    ap.add_argument("--no-multi-in-process", action="store_true", help="N > 1: skip the pcs_multi_* (one process, N GPUs) timing")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fri", action="store_true", help="skip the opening-proof (FRI) timings")
     ap.add_argument("--chunks", type=int, default=2,
@@ -335,6 +336,56 @@ def fri_opening_bench(pcs, w, lg_d, r, cap_h, dev_ptrs, steps, peak_gbs):
     }
     b.free()
     return out
+
+
+def multi_in_process_bench(a, world, cap_expected):
+    """pcs_multi_commit_from_coeffs over `world` GPUs from this ONE process (the other ranks idle at a barrier): host arm =
+    pinned host coefficients -> cap on host (each device copies its share over its own PCIe link); device arm = coefficients
+    resident, spread round-robin over the GPUs, read in place over NVLink.  Wall-clock around the synchronous calls."""
+    import torch
+
+    from helpers import splitmix64_stream
+    from plonky2_demo_b200 import _ffi
+
+    L = _ffi.lib()
+    w, lg_d, r, cap_h = a.width, a.lg_d, a.rate_bits, a.cap_height
+    d = 1 << lg_d
+    _ffi.check(L.pcs_multi_init(None, world))
+    full = torch.empty((w, d), dtype=torch.int64, pin_memory=True)
+    fn = full.numpy().view(np.uint64)
+    for j in range(w):
+        fn[j] = splitmix64_stream(0x5EED0000 + j, d)
+    hp = _ffi.ptr_array([fn[j] for j in range(w)])
+    cap = np.empty((1 << cap_h, 4), dtype=np.uint64)
+    res = {"devices": world}
+
+    def run(ptrs, flags, reps):
+        ts = []
+        for _ in range(reps):
+            h = C.c_void_p()
+            t0 = time.perf_counter()
+            _ffi.check(L.pcs_multi_commit_from_coeffs(ptrs, w, lg_d, r, cap_h, None, 0, flags, _ffi.ptr(cap), C.byref(h)))
+            ts.append(1e3 * (time.perf_counter() - t0))
+            ms5 = (C.c_float * 5)()
+            _ffi.check(L.pcs_multi_batch_timings(h, ms5))
+            L.pcs_multi_batch_free(h)
+        return ts, list(ms5)
+
+    ts, ph = run(hp, 0, 2 + a.steps)
+    res["host_inputs"] = {"ms": float(np.median(ts[2:])), "ms_min": float(min(ts[2:])), "cap_equal": bool(np.array_equal(cap, cap_expected)),
+                          "phase_ms_max_over_devices": {"FFT + blinding (incl. waits for H2D)": ph[1], "leaf hashing": ph[3], "node levels": ph[4]}}
+    tens = [torch.from_numpy(fn[j].view(np.int64)).to(f"cuda:{j % world}") for j in range(w)]
+    for g in range(world):
+        torch.cuda.synchronize(g)
+    dp = (_ffi.u64p * w)(*[C.cast(C.c_void_p(t.data_ptr()), _ffi.u64p) for t in tens])
+    ts, ph = run(dp, _ffi.PCS_DEVICE_PTRS, 2 + a.steps)
+    res["device_inputs"] = {"ms": float(np.median(ts[2:])), "ms_min": float(min(ts[2:])), "cap_equal": bool(np.array_equal(cap, cap_expected)),
+                            "elems_per_s": w * (d << r) / (float(np.median(ts[2:])) * 1e-3),
+                            "phase_ms_max_over_devices": {"FFT + blinding (peer loads)": ph[1], "leaf hashing": ph[3], "node levels": ph[4]}}
+    res["note"] = ("one process, one worker thread per GPU inside libpcs.so; exchange = first NTT pass reads the other GPUs' coefficient "
+                   "blocks over NVLink (no collective); wall-clock of the synchronous C call incl. the cap D2H")
+    del tens, full
+    return res
 
 
 def large_commit_bench(a, world, rank, dev, stream, lg_d=24):
@@ -730,6 +781,15 @@ def run_ours(a):
         dist.barrier()
     parity["lg_d_sample"] = lg_s
     out["parity_check"] = parity
+
+    # ---- the same commitment through pcs_multi_*: ONE host process (rank 0) driving all N GPUs through the C ABI, the way a
+    #      Rust prover would (no torch.distributed, no NCCL: peer loads fused into the first NTT pass) ----
+    if world > 1 and not a.no_multi_in_process:
+        dist.barrier()
+        torch.cuda.synchronize()
+        if rank == 0:
+            out["kernels"]["multi_in_process"] = multi_in_process_bench(a, world, cap_dev)
+        dist.barrier()
 
     # ---- BASELINE configs[4]: one 135 x 2^24 commitment over the whole box ----
     if world > 1 and (a.large_commit == "on" or (a.large_commit == "auto" and world == 8 and lg_d == 20 and w == 135)):
