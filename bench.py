@@ -79,9 +79,9 @@ def parse():
     ap.add_argument("--no-multi-in-process", action="store_true", help="N > 1: skip the pcs_multi_* (one process, N GPUs) timing")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fri", action="store_true", help="skip the opening-proof (FRI) timings")
-    ap.add_argument("--chunks", type=int, default=2,
+    ap.add_argument("--chunks", type=int, default=4,
                     help="N > 1: polynomial groups of the streaming exchange (1 = one all-gather, then the LDE)")
-    ap.add_argument("--e2e-chunks", type=int, default=4,
+    ap.add_argument("--e2e-chunks", type=int, default=5,
                     help="N > 1: polynomial groups of the streaming exchange in the END-TO-END arm, where every chunk also crosses "
                          "PCIe first: more, smaller chunks expose less of the first copy (2 GPUs: 68.4 ms with 4 against 70.4 ms with 2)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer"],
@@ -717,7 +717,10 @@ def run_ours(a):
     # per rank and commit: LDE passes (once per polynomial group of the streaming exchange) + leaf hashing + node levels
     lde_groups = plan.chunks if world > 1 else 1
     local_levels = (lg_d + plan.lg_cosets - plan.local_cap_height) if world > 1 else (lg_d + r - cap_h)
-    launches_per_step = lg_passes * lde_groups + 1 + local_levels
+    # node levels: one launch per level while a level has more than 256 nodes per cap subtree, then ONE launch for the top of
+    # every subtree; leaf hashing: one launch, or one per polynomial group of the streaming exchange (streaming sponge)
+    node_launches = max(local_levels - 9, 0) + (1 if local_levels >= 1 else 0)
+    launches_per_step = lg_passes * lde_groups + lde_groups + node_launches
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -109,6 +109,9 @@ PCS_API int pcs_coset_intt(uint64_t* values /*[w][n] in/out*/, size_t w, unsigne
 /* The same transform in place on a DEVICE matrix [w][n] (natural order in and out), asynchronous on
  * pcs_stream(): the per-GPU IFFT of a polynomial-partitioned from_values.                */
 PCS_API int pcs_ntt_dev(uint64_t* polys_dev, size_t w, unsigned lg_n, int inverse);
+/* pcs_coset_intt in place on a DEVICE matrix [w][n], asynchronous on pcs_stream(): the quotient polynomials'
+ * coset_ifft (plonk/prover.rs:739-743) when their values were computed on, or already copied to, the device.  */
+PCS_API int pcs_coset_intt_dev(uint64_t* values_dev, size_t w, unsigned lg_n, uint64_t shift);
 /* PolynomialBatch::lde_values (no salts): p.lde(rate_bits).coset_fft_with_options(shift, Some(rate_bits), ..)
  * for every polynomial.                                           plonky2/src/fri/oracle.rs:100-118
  * layout 0: out[w][N] natural order (== the reference's Vec<Vec<F>>);
@@ -190,6 +193,13 @@ PCS_API int pcs_batch_leaves(const pcs_batch* b, size_t first, size_t count, uin
 /* MerkleTree::get for many indices at once (merkle_tree.rs:168); get_lde_values(i, step) is
  * leaf index reverse_bits(i*step, log2 N) minus the salt columns (oracle.rs:128-133).              */
 PCS_API int pcs_batch_get_rows(const pcs_batch* b, const uint64_t* leaf_indices, size_t n, uint64_t* rows /*[n][leaf_len]*/);
+/* get_lde_values(index_start + k, step) for k = 0 .. count-1 in ONE call: rows[k][0..w) = the LDE values of every
+ * polynomial at the (index_start + k) * step -th point of the NATURAL-order domain, salt columns dropped
+ * (oracle.rs:128-133: leaf reverse_bits(index * step, log2 N)); step is a power of two.  This is the access pattern of
+ * compute_quotient_polys (plonk/prover.rs:576-744: batches of 32 consecutive points through get_lde_values_packed,
+ * oracle.rs:137-159) -- one call per oracle can serve the whole loop, or a window of it.  Rows are gathered on the device
+ * and streamed to the host in 16 MB pieces through pinned double buffering.                                        */
+PCS_API int pcs_batch_lde_natural(const pcs_batch* b, size_t index_start, size_t step, size_t count, uint64_t* rows /*[count][w]*/);
 /* MerkleTree::prove(leaf_index): siblings bottom-up, [log2 N - cap_height][4].  merkle_tree.rs:173-207 */
 PCS_API int pcs_batch_prove(const pcs_batch* b, size_t leaf_index, uint64_t* siblings);
 /* The same for n leaves in one call: siblings [n][log2 N - cap_height][4] (the FRI query phase asks every tree for

@@ -31,6 +31,7 @@ SIGNATURES = {
     "pcs_ntt": (C.c_int, [u64p, sz, C.c_uint, C.c_int]),
     "pcs_coset_intt": (C.c_int, [u64p, sz, C.c_uint, C.c_uint64]),
     "pcs_ntt_dev": (C.c_int, [C.c_void_p, sz, C.c_uint, C.c_int]),
+    "pcs_coset_intt_dev": (C.c_int, [C.c_void_p, sz, C.c_uint, C.c_uint64]),
     "pcs_coset_lde": (C.c_int, [u64pp, sz, C.c_uint, C.c_uint, C.c_uint64, u64p, C.c_int]),
     "pcs_coset_lde_dev": (C.c_int, [u64pp, sz, C.c_uint, C.c_uint, C.c_uint64, C.c_void_p]),
     "pcs_merkle_build": (C.c_int, [u64p, sz, sz, C.c_uint, u64p, u64p]),
@@ -47,6 +48,7 @@ SIGNATURES = {
     "pcs_batch_digests": (C.c_int, [C.c_void_p, u64p]),
     "pcs_batch_leaves": (C.c_int, [C.c_void_p, sz, sz, u64p]),
     "pcs_batch_get_rows": (C.c_int, [C.c_void_p, u64p, sz, u64p]),
+    "pcs_batch_lde_natural": (C.c_int, [C.c_void_p, sz, sz, sz, u64p]),
     "pcs_batch_prove": (C.c_int, [C.c_void_p, sz, u64p]),
     "pcs_batch_prove_many": (C.c_int, [C.c_void_p, u64p, sz, u64p]),
     "pcs_batch_coeffs": (C.c_int, [C.c_void_p, sz, u64p]),

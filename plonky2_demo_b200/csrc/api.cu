@@ -13,7 +13,7 @@ namespace pcs {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 
-struct PendingEvents { cudaEvent_t ev[6]; };
+struct PendingEvents { cudaEvent_t ev[6]; std::vector<cudaEvent_t> absorb_ev; };
 
 struct Ctx {
     std::vector<PendingEvents> pending;   // events of freed batches, not yet folded into totals
@@ -65,11 +65,19 @@ static void drain_pending() {
         bool ok = true;
         float ms[5];
         for (int i = 0; i < 5 && ok; i++) ok = cudaEventElapsedTime(&ms[i], pe.ev[i], pe.ev[i + 1]) == cudaSuccess;
+        // leaf hashing that ran group by group inside the "FFT + blinding" phase (streaming sponge) is booked as leaf hashing
+        for (size_t k = 0; k + 1 < pe.absorb_ev.size() && ok; k += 2) {
+            float t = 0;
+            ok = cudaEventElapsedTime(&t, pe.absorb_ev[k], pe.absorb_ev[k + 1]) == cudaSuccess;
+            ms[1] -= t;
+            ms[3] += t;
+        }
         if (ok) {
             for (int i = 0; i < 5; i++) g_ctx.totals[i] += ms[i];
             g_ctx.n_totals++;
         }
         for (auto& e : pe.ev) cudaEventDestroy(e);
+        for (auto& e : pe.absorb_ev) cudaEventDestroy(e);
     }
     g_ctx.pending.clear();
     cudaGetLastError();
@@ -101,14 +109,50 @@ pcs_batch* batch_new() {
         }                                                                          \
     } while (0)
 
+static int node_levels_dev(size_t n, unsigned lg_sub, uint64_t* digests, uint64_t* cap, cudaStream_t st) {
+    // one launch per level while a level still fills the GPU (more than 256 nodes per cap subtree), then the top of every
+    // subtree in ONE launch
+    unsigned level = 1;
+    for (; level <= lg_sub && lg_sub - level > 8; level++)
+        PCS_CUDA(launch_node_level(digests, cap, lg_sub, level, n >> level, st));
+    if (level <= lg_sub) PCS_CUDA(launch_node_top(digests, cap, lg_sub, level, n >> lg_sub, st));
+    return PCS_OK;
+}
+
 // leaf digests + all node levels; cols = [width][n] poly-major
 int build_tree_dev(const uint64_t* cols, size_t n, size_t width, unsigned lg_n, unsigned cap_height,
                           uint64_t* digests, uint64_t* cap, cudaStream_t st, cudaEvent_t after_leaves) {
     unsigned lg_sub = lg_n - cap_height;
     PCS_CUDA(launch_leaf_hash_cols(cols, n, (uint32_t)width, n, lg_sub, digests, cap, st));
     if (after_leaves) PCS_CUDA(cudaEventRecord(after_leaves, st));
-    for (unsigned level = 1; level <= lg_sub; level++)
-        PCS_CUDA(launch_node_level(digests, cap, lg_sub, level, n >> level, st));
+    return node_levels_dev(n, lg_sub, digests, cap, st);
+}
+
+// Streaming sponge: absorb the LDE columns [b->absorbed, upto) of every leaf (upto a multiple of the rate, or all columns
+// with last = true, which also emits the digests).  timed: bracket the launch with an event pair (absorbs that run inside the
+// "FFT + blinding" phase are booked as leaf hashing by the timing queries).
+static int absorb_columns(pcs_batch* b, size_t upto, bool last, cudaStream_t st, bool timed) {
+    if (upto < b->absorbed) return fail(PCS_ERR_ARG, "internal: sponge cannot go backwards");
+    if (upto == b->absorbed && !last) return PCS_OK;
+    const bool first = b->absorbed == 0;
+    const unsigned lg_sub = b->lg_d + b->rate_bits - b->cap_height;
+    if (!(first && last) && !b->sponge) PCS_CUDA(cudaMallocAsync((void**)&b->sponge, 12 * b->n * 8, st));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timed) {
+        PCS_CUDA(cudaEventCreate(&e0));
+        PCS_CUDA(cudaEventCreate(&e1));
+        b->absorb_ev.push_back(e0);
+        b->absorb_ev.push_back(e1);
+        PCS_CUDA(cudaEventRecord(e0, st));
+    }
+    PCS_CUDA(launch_leaf_hash_group(b->lde + b->absorbed * b->n, b->n, (uint32_t)(upto - b->absorbed), b->n, first, last, b->sponge,
+                                    lg_sub, b->digests, b->cap, st));
+    if (timed) PCS_CUDA(cudaEventRecord(e1, st));
+    b->absorbed = upto;
+    if (last && b->sponge) {
+        cudaFreeAsync(b->sponge, st);
+        b->sponge = nullptr;
+    }
     return PCS_OK;
 }
 
@@ -379,6 +423,24 @@ int pcs_coset_intt(uint64_t* values, size_t w, unsigned lg_n, uint64_t shift) {
     return PCS_OK;
 }
 
+int pcs_coset_intt_dev(uint64_t* values_dev, size_t w, unsigned lg_n, uint64_t shift) {
+    PCS_NEED_INIT();
+    if (w == 0) return PCS_OK;
+    if (!values_dev) return fail(PCS_ERR_ARG, "values is NULL");
+    if (lg_n > 32) return fail(PCS_ERR_TWO_ADICITY, "n_log <= TWO_ADICITY violated");
+    if (shift % 0xFFFFFFFF00000001ULL == 0) return fail(PCS_ERR_ARG, "shift must be non-zero");
+    cudaStream_t st = g_ctx.stream;
+    size_t n = (size_t)1 << lg_n;
+    NttPlan* plan = ntt_plan_get(lg_n, 0, true, 1, st);
+    if (!plan) return fail(PCS_ERR_ALLOC, "twiddle table allocation failed");
+    DevBuf b;
+    PCS_CUDA(b.alloc(w * n * 8, st));
+    PCS_CUDA(ntt_lde(plan, values_dev, n, b.u64(), n, w, st));                                             // -> bit-reversed
+    PCS_CUDA(launch_bitrev_permute(b.u64(), n, values_dev, n, w, lg_n, st, ntt_plan_scale(plan)));         // -> natural, * 1/n
+    PCS_CUDA(launch_mul_powers(values_dev, n, w, n, host_inverse(shift), st));                             // c_i *= shift^-i
+    return PCS_OK;   // asynchronous on pcs_stream()
+}
+
 int pcs_ntt_dev(uint64_t* polys_dev, size_t w, unsigned lg_n, int inverse) {
     PCS_NEED_INIT();
     if (w == 0) return PCS_OK;
@@ -413,6 +475,11 @@ static void* pinned(void*& buf, size_t& cap, size_t bytes) {
     }
     return buf;
 }
+
+// Device -> pageable host memory: D2H into one of two pinned buffers, then a multi-threaded copy into the caller's memory
+// (fresh Vecs / numpy arrays fault their pages on first touch: one thread moves ~5 GB/s, four ~15) while the next piece is
+// already crossing PCIe.  Synchronises the stream.
+static int d2h_pageable(void* dst, const void* src_dev, size_t bytes, cudaStream_t st);
 
 constexpr size_t RING_SLOT_BYTES = 16u << 20;
 constexpr unsigned STAGE_THREADS = 4;
@@ -477,6 +544,51 @@ static int stage_polys(const uint64_t* const* polys, size_t w, size_t d, bool de
         if (!polys[j]) return fail(PCS_ERR_ARG, "NULL polynomial pointer");
         PCS_CUDA(cudaMemcpyAsync(dst + j * d, polys[j], d * 8, device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     }
+    return PCS_OK;
+}
+
+static void host_copy_mt(char* dst, const char* src, size_t bytes) {
+    const unsigned nt = bytes >= (4u << 20) ? STAGE_THREADS : 1;
+    if (nt == 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::thread th[STAGE_THREADS];
+    const size_t per = (bytes / nt + 4095) & ~(size_t)4095;
+    for (unsigned t = 0; t < nt; t++) {
+        const size_t o = (size_t)t * per, l = o >= bytes ? 0 : (bytes - o < per ? bytes - o : per);
+        th[t] = std::thread([=]() { if (l) memcpy(dst + o, src + o, l); });
+    }
+    for (unsigned t = 0; t < nt; t++) th[t].join();
+}
+
+static int d2h_pageable(void* dst, const void* src_dev, size_t bytes, cudaStream_t st) {
+    const size_t PIECE = 16u << 20;
+    if (bytes <= (1u << 20) || !is_pageable_host(dst)) {
+        PCS_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+        PCS_CUDA(cudaStreamSynchronize(st));
+        return PCS_OK;
+    }
+    if (!pinned(g_ctx.pin_out, g_ctx.pin_out_bytes, 2 * PIECE)) return fail(PCS_ERR_ALLOC, "pinned staging allocation failed");
+    cudaEvent_t ev[2];
+    PCS_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    PCS_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    struct EvGuard { cudaEvent_t* e; ~EvGuard() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } evg{ev};
+    size_t prev_off = 0, prev_len = 0;
+    int slot = 0;
+    for (size_t off = 0; off < bytes; off += PIECE, slot ^= 1) {
+        const size_t len = bytes - off < PIECE ? bytes - off : PIECE;
+        PCS_CUDA(cudaMemcpyAsync((char*)g_ctx.pin_out + (size_t)slot * PIECE, (const char*)src_dev + off, len, cudaMemcpyDeviceToHost, st));
+        PCS_CUDA(cudaEventRecord(ev[slot], st));
+        if (prev_len) {
+            PCS_CUDA(cudaEventSynchronize(ev[slot ^ 1]));
+            host_copy_mt((char*)dst + prev_off, (char*)g_ctx.pin_out + (size_t)(slot ^ 1) * PIECE, prev_len);
+        }
+        prev_off = off;
+        prev_len = len;
+    }
+    PCS_CUDA(cudaEventSynchronize(ev[slot ^ 1]));
+    host_copy_mt((char*)dst + prev_off, (char*)g_ctx.pin_out + (size_t)(slot ^ 1) * PIECE, prev_len);
     return PCS_OK;
 }
 
@@ -580,9 +692,11 @@ void pcs_batch_free(pcs_batch* b) {
     if (b->lde) cudaFreeAsync(b->lde, st);
     if (b->digests) cudaFreeAsync(b->digests, st);
     if (b->cap) cudaFreeAsync(b->cap, st);
+    if (b->sponge) cudaFreeAsync(b->sponge, st);
     if (b->ev[5] && b->committed) {
         PendingEvents pe;
         for (int i = 0; i < 6; i++) pe.ev[i] = b->ev[i];
+        pe.absorb_ev.swap(b->absorb_ev);
         g_ctx.pending.push_back(pe);
         if (g_ctx.pending.size() > 256) {
             cudaStreamSynchronize(st);
@@ -592,6 +706,7 @@ void pcs_batch_free(pcs_batch* b) {
         for (auto& e : b->ev)
             if (e) cudaEventDestroy(e);
     }
+    for (auto& e : b->absorb_ev) cudaEventDestroy(e);
     delete b;
 }
 
@@ -652,7 +767,7 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
     DevBuf ptr_table;                // or: device table of the caller's w polynomial pointers, read in place
     uint64_t* staged = nullptr;
     bool scatter_coeffs = false;
-    size_t H2D_CHUNK = 16;            // polynomials per H2D chunk
+    std::vector<size_t> cb;           // chunk k = polynomials [cb[k], cb[k+1]) of the host-input pipeline
     size_t n_chunks = 0;              // > 0: host inputs arrive chunk by chunk on the copy stream
     bool pageable = false;            // ... through the pinned ring, each chunk staged right before its compute is enqueued
     if (contiguous_dev && !from_values && !(flags & PCS_KEEP_COEFFS)) {
@@ -688,8 +803,16 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
                 if (!polys[j]) return fail(PCS_ERR_ARG, "NULL polynomial pointer");
             pageable = w * d * 8 >= (8u << 20) && is_pageable_host(polys[0]);   // below 8 MB the threads cost more than they save
             // pageable inputs: a chunk fills one ring slot, so that the staging threads are started once per 16 MB
-            if (pageable && H2D_CHUNK * d * 8 < RING_SLOT_BYTES) H2D_CHUNK = RING_SLOT_BYTES / (d * 8);
-            n_chunks = (w + H2D_CHUNK - 1) / H2D_CHUNK;
+            // Chunk sizes: the first transfer is the only one nothing hides, so it is small (8 polynomials = one absorb of the
+            // sponge, or one 16 MB ring slot's worth for short polynomials); a chunk's compute (LDE + its share of the leaf
+            // hashing, ~0.9 ms per polynomial at 2^20) outlasts a transfer 5x its size, so the groups grow 5x and few sponge
+            // states have to be parked (each group boundary costs 192 B of HBM traffic per leaf).
+            size_t first = 8;
+            if (first * d * 8 < RING_SLOT_BYTES) first = (RING_SLOT_BYTES / (d * 8) + 7) / 8 * 8;
+            cb.assign(1, 0);
+            for (size_t sz = first; cb.back() < w; sz *= 5) cb.push_back(cb.back() + sz < w ? cb.back() + sz : w);
+            if (cb.size() > 2 && w - cb[cb.size() - 2] < 8) cb.erase(cb.end() - 2);   // no tiny tail group
+            n_chunks = cb.size() - 1;
             while (g_ctx.chunk_ev.size() < n_chunks) {
                 cudaEvent_t e;
                 PCS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -699,7 +822,7 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
             PCS_CUDA(cudaStreamWaitEvent(g_ctx.copy_stream, g_ctx.ev_sync, 0));
             copy_drain.armed = true;
             for (size_t k = 0; k < n_chunks && !pageable; k++) {
-                size_t j0 = k * H2D_CHUNK, j1 = j0 + H2D_CHUNK < w ? j0 + H2D_CHUNK : w;
+                size_t j0 = cb[k], j1 = cb[k + 1];
                 int rc = stage_polys(polys + j0, j1 - j0, d, false, staged + j0 * d, g_ctx.copy_stream);
                 if (rc) {
                     cudaStreamSynchronize(g_ctx.copy_stream);   // `staged` is released by the guard
@@ -737,7 +860,7 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
     // ---- "FFT + blinding" (oracle.rs:100-125), output already in leaf order ----
     if (chunked) {
         for (size_t k = 0; k < n_chunks; k++) {
-            size_t j0 = k * H2D_CHUNK, j1 = j0 + H2D_CHUNK < w ? j0 + H2D_CHUNK : w;
+            size_t j0 = cb[k], j1 = cb[k + 1];
             if (pageable) {
                 int rc = stage_pageable(polys + j0, j1 - j0, d, staged + j0 * d, g_ctx.copy_stream);
                 if (rc) {
@@ -752,6 +875,13 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
                 if (rc) return rc;
             }
             PCS_CUDA(ntt_lde_cosets(plan, src + j0 * d, d, b->lde + j0 * n, n, j1 - j0, coset_first, lg_cosets, st));
+            // streaming sponge: hash what has landed while the next chunks are still crossing PCIe (the last group is absorbed
+            // by "build Merkle tree" below, together with the salt columns)
+            b->extended = j1;
+            if (wt > 4 && j1 < w) {
+                int rc = absorb_columns(b, (j1 / 8) * 8, false, st, true);
+                if (rc) return rc;
+            }
         }
     } else {
         PCS_CUDA(ntt_lde_cosets(plan, src, d, b->lde, n, w, coset_first, lg_cosets, st,
@@ -779,7 +909,15 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
     PCS_CUDA(cudaEventRecord(b->ev[3], st));
 
     // ---- "build Merkle tree" (oracle.rs:85-89) ----
-    int rc = build_tree_dev(b->lde, n, wt, lg_n, cap_height, b->digests, b->cap, st, b->ev[4]);
+    int rc;
+    if (b->absorbed > 0) {
+        rc = absorb_columns(b, wt, true, st, false);     // the remaining columns (+ salts) and the digests
+        if (rc) return rc;
+        PCS_CUDA(cudaEventRecord(b->ev[4], st));
+        rc = node_levels_dev(n, lg_n - cap_height, b->digests, b->cap, st);
+    } else {
+        rc = build_tree_dev(b->lde, n, wt, lg_n, cap_height, b->digests, b->cap, st, b->ev[4]);
+    }
     if (rc) return rc;
     PCS_CUDA(cudaEventRecord(b->ev[5], st));
 
@@ -930,6 +1068,14 @@ int pcs_shard_extend(pcs_batch* b, size_t poly_first, size_t count, const uint64
         }
     }
     PCS_CUDA(ntt_lde_cosets(plan, src, d, b->lde + poly_first * b->n, b->n, count, b->coset_first, b->rate_bits, st, ptrs));
+    // streaming sponge: groups that arrive in order are hashed at once (while the next group's coefficients are still in
+    // flight); a shard that gets all its polynomials in one call keeps the single hash kernel of pcs_shard_finish
+    if (poly_first == b->extended) b->extended += count;
+    const bool whole = poly_first == 0 && count == b->w;
+    if (!whole && b->w + b->salt_w > 4 && b->extended < b->w) {
+        int rc = absorb_columns(b, (b->extended / 8) * 8, false, st, true);
+        if (rc) return rc;
+    }
     return PCS_OK;   // asynchronous on pcs_stream()
 }
 
@@ -940,7 +1086,15 @@ int pcs_shard_finish(pcs_batch* b, uint64_t* cap_out) {
     cudaStream_t st = g_ctx.stream;
     PCS_CUDA(cudaEventRecord(b->ev[2], st));
     PCS_CUDA(cudaEventRecord(b->ev[3], st));
-    int rc = build_tree_dev(b->lde, b->n, b->w + b->salt_w, b->lg_d + b->rate_bits, b->cap_height, b->digests, b->cap, st, b->ev[4]);
+    int rc;
+    if (b->absorbed > 0) {
+        rc = absorb_columns(b, b->w + b->salt_w, true, st, false);
+        if (rc) return rc;
+        PCS_CUDA(cudaEventRecord(b->ev[4], st));
+        rc = node_levels_dev(b->n, b->lg_d + b->rate_bits - b->cap_height, b->digests, b->cap, st);
+    } else {
+        rc = build_tree_dev(b->lde, b->n, b->w + b->salt_w, b->lg_d + b->rate_bits, b->cap_height, b->digests, b->cap, st, b->ev[4]);
+    }
     if (rc) return rc;
     PCS_CUDA(cudaEventRecord(b->ev[5], st));
     b->committed = true;
@@ -994,15 +1148,15 @@ int pcs_batch_leaves(const pcs_batch* b, size_t first, size_t count, uint64_t* r
     cudaStream_t st = g_ctx.stream;
     size_t wt = b->w + b->salt_w;
     // transpose in slabs so that the staging buffer stays small
-    const size_t slab = (size_t)1 << 20;
+    const size_t slab = (size_t)1 << 18;
     DevBuf tmp;
     PCS_CUDA(tmp.alloc((count < slab ? count : slab) * wt * 8, st));
     for (size_t off = 0; off < count; off += slab) {
         size_t c = count - off < slab ? count - off : slab;
         PCS_CUDA(launch_transpose(b->lde + first + off, b->n, tmp.u64(), wt, wt, c, st));
-        PCS_CUDA(cudaMemcpyAsync(rows + off * wt, tmp.p, c * wt * 8, cudaMemcpyDeviceToHost, st));
+        int rc = d2h_pageable(rows + off * wt, tmp.p, c * wt * 8, st);
+        if (rc) return rc;
     }
-    PCS_CUDA(cudaStreamSynchronize(st));
     return PCS_OK;
 }
 
@@ -1021,6 +1175,32 @@ int pcs_batch_get_rows(const pcs_batch* b, const uint64_t* leaf_indices, size_t 
     PCS_CUDA(launch_gather_rows(b->lde, b->n, (uint32_t)wt, idx.u64(), n, o.u64(), st));
     PCS_CUDA(cudaMemcpyAsync(rows, o.p, n * wt * 8, cudaMemcpyDeviceToHost, st));
     PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+int pcs_batch_lde_natural(const pcs_batch* b, size_t index_start, size_t step, size_t count, uint64_t* rows) {
+    BatchScope scope(b);
+    if (!b || (count && !rows)) return fail(PCS_ERR_ARG, "NULL pointer");
+    if (count == 0) return PCS_OK;
+    if (step == 0 || (step & (step - 1))) return fail(PCS_ERR_ARG, "step must be a power of two");
+    // (index_start + k) * step < N for every k (oracle.rs:129-130 indexes merkle_tree.leaves with the reversed product)
+    if (index_start > b->n / step || count > b->n / step - index_start) return fail(PCS_ERR_ARG, "point range out of bounds");
+    cudaStream_t st = g_ctx.stream;
+    const size_t w = b->w;                       // salt columns are dropped (oracle.rs:131-132)
+    const unsigned lg_n = b->lg_d + b->rate_bits;
+    // slabs of <= 256 MB: gather on the device, then stream to the caller's (usually pageable) rows
+    const size_t SLAB = (size_t)256 << 20;
+    size_t ch = SLAB / (w * 8);
+    if (ch < 1) ch = 1;
+    if (ch > count) ch = count;
+    DevBuf tmp;
+    PCS_CUDA(tmp.alloc(ch * w * 8, st));
+    for (size_t off = 0; off < count; off += ch) {
+        const size_t c = count - off < ch ? count - off : ch;
+        PCS_CUDA(launch_lde_natural(b->lde, b->n, (uint32_t)w, lg_n, index_start + off, step, c, tmp.u64(), st));
+        int rc = d2h_pageable(rows + off * w, tmp.p, c * w * 8, st);
+        if (rc) return rc;
+    }
     return PCS_OK;
 }
 
@@ -1091,6 +1271,12 @@ int pcs_batch_timings(const pcs_batch* b, float ms[5]) {
     if (!b || !ms) return fail(PCS_ERR_ARG, "NULL pointer");
     PCS_CUDA(cudaStreamSynchronize(g_ctx.stream));
     for (int i = 0; i < 5; i++) PCS_CUDA(cudaEventElapsedTime(&ms[i], b->ev[i], b->ev[i + 1]));
+    for (size_t k = 0; k + 1 < b->absorb_ev.size(); k += 2) {   // streamed leaf hashing ran inside the LDE phase
+        float t = 0;
+        PCS_CUDA(cudaEventElapsedTime(&t, b->absorb_ev[k], b->absorb_ev[k + 1]));
+        ms[1] -= t;
+        ms[3] += t;
+    }
     return PCS_OK;
 }
 

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "pcs.h"
 
@@ -23,6 +24,11 @@ struct pcs_batch {
     bool has_ifft = false;
     bool committed = false;  // all six events recorded
     bool rows_only = false;  // pcs_shard_begin_rows: LDE rows are supplied, not computed here
+    // streaming sponge (leaf hashing group by group while later groups are still in flight)
+    uint64_t* sponge = nullptr;      // [12][n] parked states, allocated at the first partial absorb
+    size_t absorbed = 0;             // columns [0, absorbed) are in the sponge states
+    size_t extended = 0;             // polynomials [0, extended) have their LDE rows in place (contiguous prefix)
+    std::vector<cudaEvent_t> absorb_ev;   // start/stop pairs around the absorbs that ran inside the "FFT + blinding" phase
     void* ctx = nullptr;     // the per-device engine context (api.cu) that owns the buffers: accessors and free run there
 };
 
@@ -95,12 +101,19 @@ cudaError_t launch_pow_search(const uint64_t* state_dev, unsigned pos, unsigned 
 cudaError_t launch_leaf_hash_cols(const uint64_t* cols, size_t col_stride, uint32_t width, size_t n_leaves,
                                   unsigned lg_sub /*log2 leaves per cap subtree*/, uint64_t* digests,
                                   uint64_t* cap, cudaStream_t st, size_t first_leaf = 0, size_t leaf_count = (size_t)-1);
+// One GROUP of columns of a streaming sponge: cols = first column of the group, width = columns in it (a multiple of 8 unless
+// it is the last group); state = [12][n_leaves] parked sponge states (unused when first && last).
+cudaError_t launch_leaf_hash_group(const uint64_t* cols, size_t col_stride, uint32_t width, size_t n_leaves, bool first, bool last,
+                                   uint64_t* state, unsigned lg_sub, uint64_t* digests, uint64_t* cap, cudaStream_t st);
 // Plain variant: digest i -> out[i*4..] (pcs_hash_or_noop)
 cudaError_t launch_hash_cols_plain(const uint64_t* cols, size_t col_stride, uint32_t width, size_t n,
                                    uint64_t* out, cudaStream_t st);
 // One level of two_to_one: nodes of level `level` (1 = parents of leaf digests) for all subtrees.
 cudaError_t launch_node_level(uint64_t* digests, uint64_t* cap, unsigned lg_sub, unsigned level,
                               size_t n_nodes /*total at this level*/, cudaStream_t st);
+// Levels [level_first, lg_sub] of every cap subtree in one launch (<= 256 nodes per subtree at level_first).
+cudaError_t launch_node_top(uint64_t* digests, uint64_t* cap, unsigned lg_sub, unsigned level_first, size_t n_subtrees,
+                            cudaStream_t st);
 cudaError_t launch_two_to_one(const uint64_t* l, const uint64_t* r, size_t n, uint64_t* out, cudaStream_t st);
 // Merkle path gather: siblings of leaf_index, bottom-up ([lg_sub][4]).
 cudaError_t launch_prove(const uint64_t* digests, unsigned lg_sub, size_t leaf_index, uint64_t* siblings,
@@ -147,6 +160,9 @@ cudaError_t launch_transpose(const uint64_t* in, size_t in_pitch, uint64_t* out,
 cudaError_t launch_gather_rows(const uint64_t* cols, size_t col_stride, uint32_t width, const uint64_t* idx,
                                size_t n_idx, uint64_t* out, cudaStream_t st);
 cudaError_t launch_canonicalize(uint64_t* data, size_t n, cudaStream_t st);
+// out[k][j] = cols[j][brev_{lg_n}((index_start + k) * step)], k < count, j < width
+cudaError_t launch_lde_natural(const uint64_t* cols, size_t col_stride, uint32_t width, unsigned lg_n, size_t index_start,
+                               size_t step, size_t count, uint64_t* out, cudaStream_t st);
 // data[j][i] *= base^i for j < w, i < n (row stride `stride`)
 cudaError_t launch_mul_powers(uint64_t* data, size_t stride, size_t w, size_t n, uint64_t base, cudaStream_t st);
 

@@ -45,6 +45,53 @@ k_hash_cols(const uint64_t* __restrict__ cols, size_t col_stride, uint32_t width
     o[1] = make_ulonglong2(d[2], d[3]);
 }
 
+// The same sponge absorbed in GROUPS of columns (a streaming commit: group g is hashed while group g+1 is still crossing
+// PCIe / NVLink).  The overwrite-mode sponge is sequential in the columns, so a group boundary only has to fall on a multiple
+// of the rate (8): the 12-lane state of every leaf is parked in HBM between groups ([12][n], lane-major so that loads and
+// stores stay coalesced; 96 B per leaf against 64 B per absorbed chunk -- irrelevant for a kernel at 1 % of the HBM roofline).
+//   FIRST: the state starts at zero (hashing.rs:124);  LAST: the digest (lanes 0..3, canonical) goes to the leaf's tree slot.
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(HASH_THREADS)
+k_hash_cols_stream(const uint64_t* __restrict__ cols, size_t col_stride, uint32_t width, size_t n, uint64_t* __restrict__ state,
+                   unsigned lg_sub, uint64_t* __restrict__ digests, uint64_t* __restrict__ cap) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = FIRST ? 0 : state[(size_t)k * n + i];
+    const uint64_t* p = cols + i;
+#pragma unroll 1
+    for (uint32_t j = 0; j < width; j += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (j + k < width) s[k] = __ldg(p + (size_t)(j + k) * col_stride);
+        poseidon12<false>(s);
+    }
+    if (LAST) {
+        ulonglong2* o = reinterpret_cast<ulonglong2*>(digest_slot(digests, cap, lg_sub, 0, i));
+        o[0] = make_ulonglong2(gl::canon(s[0]), gl::canon(s[1]));
+        o[1] = make_ulonglong2(gl::canon(s[2]), gl::canon(s[3]));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; k++) state[(size_t)k * n + i] = s[k];
+    }
+}
+
+cudaError_t launch_leaf_hash_group(const uint64_t* cols, size_t col_stride, uint32_t width, size_t n_leaves, bool first, bool last,
+                                   uint64_t* state, unsigned lg_sub, uint64_t* digests, uint64_t* cap, cudaStream_t st) {
+    if (n_leaves == 0) return cudaSuccess;
+    const unsigned grid = grid_for(n_leaves, HASH_THREADS);
+    if (first && last)
+        k_hash_cols_stream<true, true><<<grid, HASH_THREADS, 0, st>>>(cols, col_stride, width, n_leaves, state, lg_sub, digests, cap);
+    else if (first)
+        k_hash_cols_stream<true, false><<<grid, HASH_THREADS, 0, st>>>(cols, col_stride, width, n_leaves, state, lg_sub, digests, cap);
+    else if (last)
+        k_hash_cols_stream<false, true><<<grid, HASH_THREADS, 0, st>>>(cols, col_stride, width, n_leaves, state, lg_sub, digests, cap);
+    else
+        k_hash_cols_stream<false, false><<<grid, HASH_THREADS, 0, st>>>(cols, col_stride, width, n_leaves, state, lg_sub, digests, cap);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_leaf_hash_cols(const uint64_t* cols, size_t col_stride, uint32_t width, size_t n_leaves,
                                   unsigned lg_sub, uint64_t* digests, uint64_t* cap, cudaStream_t st,
                                   size_t first_leaf, size_t leaf_count) {

@@ -80,12 +80,27 @@ size_t block_bytes(size_t rows, size_t d) { return (rows ? rows : 1) * d * 8; }
 struct Plan {
     int G;
     unsigned lg_dev, lg_cosets, local_cap_height, top_levels;
-    size_t chunks, w_chunk;
+    size_t chunks;
     size_t w;
+    std::vector<size_t> bounds;   // chunk c = polynomials [bounds[c], bounds[c+1])
+    // Groups for the streaming pipeline: the first one small (its transfer is the only one nothing hides), the rest equal
+    // multiples of the sponge rate 8 so that every group can be hashed as soon as it is extended.
+    void make_chunks(size_t k) {
+        bounds.assign(1, 0);
+        if (k <= 1 || w <= 16) {
+            bounds.push_back(w);
+        } else {
+            size_t per = (w - 8 + (k - 2)) / (k - 1);
+            per = (per + 7) / 8 * 8;
+            bounds.push_back(8);
+            while (bounds.back() < w) bounds.push_back(bounds.back() + per < w ? bounds.back() + per : w);
+        }
+        chunks = bounds.size() - 1;
+    }
     // polynomials [lo, hi) of chunk c; device g holds rows [lo + g m, min(lo + (g+1) m, hi)) of it, m = ceil((hi-lo)/G)
     void chunk_range(size_t c, size_t& lo, size_t& hi) const {
-        lo = c * w_chunk < w ? c * w_chunk : w;
-        hi = lo + w_chunk < w ? lo + w_chunk : w;
+        lo = bounds[c];
+        hi = bounds[c + 1];
     }
     void part(size_t c, int g, size_t& a, size_t& b) const {
         size_t lo, hi;
@@ -250,14 +265,14 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
     const size_t d = (size_t)1 << lg_d, n = d << rate_bits, n_loc = n >> plan.lg_dev;
     // device-resident inputs are read in place; host inputs arrive in chunks (H2D of chunk c+1 under the LDE of chunk c)
     const bool staged = !dev_ptrs || from_values;   // from_values transforms in place: always on engine-owned blocks
-    plan.chunks = 1;
+    size_t want_chunks = 1;
     if (staged && !from_values && !dev_ptrs) {
-        size_t by_size = (w * d * 8) >> 24;          // ~16 MB per device and chunk at least
-        plan.chunks = by_size / G < 1 ? 1 : by_size / G;
-        if (plan.chunks > 4) plan.chunks = 4;
-        if (plan.chunks > w) plan.chunks = w;
+        size_t by_size = (w * d * 8) >> 23;          // ~8 MB per device and chunk at least
+        want_chunks = by_size / G < 1 ? 1 : by_size / G;
+        if (want_chunks > MULTI_MAX_CHUNKS - 2) want_chunks = MULTI_MAX_CHUNKS - 2;
     }
-    plan.w_chunk = (w + plan.chunks - 1) / plan.chunks;
+    plan.make_chunks(want_chunks);
+    if (plan.chunks > MULTI_MAX_CHUNKS) return fail(PCS_ERR_ARG, "internal: too many chunks");
     const size_t n_local_cap = (size_t)1 << plan.local_cap_height;
 
     pcs_multi_batch* mb = new pcs_multi_batch();

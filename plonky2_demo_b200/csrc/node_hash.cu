@@ -38,6 +38,42 @@ k_compress(uint64_t* __restrict__ a, uint64_t* __restrict__ b, uint64_t* __restr
     o[1] = make_ulonglong2(gl::canon(s[2]), gl::canon(s[3]));
 }
 
+// The TOP of every cap subtree in one launch: levels [level_first, lg_sub] with at most 256 nodes per subtree at level_first.
+// One CTA per subtree; a level's nodes are written to the digest array by this CTA and read back by it for the next level
+// (__syncthreads orders the global accesses inside the block).  Replaces up to 9 latency-bound launches of k_compress --
+// what is left of the tree once the levels are too small to fill the GPU (0.3-0.4 ms of a sharded commit, most of a small one).
+__global__ void __launch_bounds__(256)
+k_compress_top(uint64_t* __restrict__ digests, uint64_t* __restrict__ cap, unsigned lg_sub, unsigned level_first) {
+    const size_t sub = blockIdx.x;
+    for (unsigned level = level_first; level <= lg_sub; level++) {
+        const unsigned per = 1u << (lg_sub - level);      // nodes of this subtree at this level
+        if (threadIdx.x < per) {
+            const size_t k = (sub << (lg_sub - level)) + threadIdx.x;
+            const ulonglong2* l = reinterpret_cast<const ulonglong2*>(digest_slot(digests, cap, lg_sub, level - 1, 2 * k));
+            const ulonglong2* r = l + 2;
+            ulonglong2 v0 = l[0], v1 = l[1], v2 = r[0], v3 = r[1];
+            uint64_t s[12];
+            s[0] = v0.x; s[1] = v0.y; s[2] = v1.x; s[3] = v1.y;
+            s[4] = v2.x; s[5] = v2.y; s[6] = v3.x; s[7] = v3.y;
+            s[8] = s[9] = s[10] = s[11] = 0;
+            poseidon12<false>(s);
+            ulonglong2* o = reinterpret_cast<ulonglong2*>(digest_slot(digests, cap, lg_sub, level, k));
+            o[0] = make_ulonglong2(gl::canon(s[0]), gl::canon(s[1]));
+            o[1] = make_ulonglong2(gl::canon(s[2]), gl::canon(s[3]));
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_node_top(uint64_t* digests, uint64_t* cap, unsigned lg_sub, unsigned level_first, size_t n_subtrees,
+                            cudaStream_t st) {
+    if (n_subtrees == 0 || level_first > lg_sub) return cudaSuccess;
+    if (lg_sub - level_first > 8) return cudaErrorInvalidValue;
+    const unsigned threads = 1u << (lg_sub - level_first) < 32 ? 32 : 1u << (lg_sub - level_first);
+    k_compress_top<<<(unsigned)n_subtrees, threads, 0, st>>>(digests, cap, lg_sub, level_first);
+    return cudaGetLastError();
+}
+
 // MerkleTree::prove: one thread per layer copies the sibling digest.
 __global__ void k_prove(const uint64_t* __restrict__ digests, unsigned lg_sub, size_t leaf_index,
                         uint64_t* __restrict__ siblings) {

@@ -562,14 +562,43 @@ cudaError_t launch_bitrev_gather(const uint64_t* in, unsigned lg_n, size_t first
 
 uint64_t ntt_plan_scale(const NttPlan* plan) { return plan->scale; }
 
+// The same permutation with both sides coalesced (lg_n >= 10): the index is [hi (5 bits) | mid | lo (5 bits)] and
+// brev(i) = [brev(lo) | brev(mid) | brev(hi)], so for a fixed mid the 32 x 32 values (hi, lo) are read as 32 contiguous
+// runs over lo and written as 32 contiguous runs over brev(hi): one shared-memory transpose per tile.
+__global__ void __launch_bounds__(256) k_bitrev_permute_tiled(const uint64_t* __restrict__ in, size_t in_stride,
+                                                             uint64_t* __restrict__ out, size_t out_stride, unsigned lg_n,
+                                                             uint64_t scale) {
+    __shared__ uint64_t t[32][33];
+    const unsigned m = lg_n - 10;
+    const size_t mid = blockIdx.x, j = blockIdx.y;
+    const uint64_t* src = in + j * in_stride;
+    uint64_t* dst = out + j * out_stride;
+    const unsigned x = threadIdx.x;
+    for (unsigned hi = threadIdx.y; hi < 32; hi += 8) {
+        uint64_t v = src[((size_t)hi << (m + 5)) | (mid << 5) | x];
+        if (scale != 1) v = gl::canon(gl::mul(v, scale));
+        t[hi][x] = v;
+    }
+    __syncthreads();
+    const size_t rmid = m ? (size_t)(__brevll((unsigned long long)mid) >> (64 - m)) : 0;
+    const unsigned hi_src = __brev(x) >> 27;
+    for (unsigned lo = threadIdx.y; lo < 32; lo += 8)
+        dst[((size_t)(__brev(lo) >> 27) << (m + 5)) | (rmid << 5) | x] = t[hi_src][lo];
+}
+
 cudaError_t launch_bitrev_permute(const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride, size_t w,
                                   unsigned lg_n, cudaStream_t st, uint64_t scale) {
     if (w == 0) return cudaSuccess;
     size_t n = (size_t)1 << lg_n;
     for (size_t j0 = 0; j0 < w; j0 += 65535) {
         size_t wj = w - j0 < 65535 ? w - j0 : 65535;
-        dim3 grid((unsigned)((n + 255) / 256), (unsigned)wj);
-        k_bitrev_permute<<<grid, 256, 0, st>>>(in + j0 * in_stride, in_stride, out + j0 * out_stride, out_stride, lg_n, scale);
+        if (lg_n >= 10 && lg_n <= 40) {
+            dim3 grid((unsigned)(n >> 10), (unsigned)wj);
+            k_bitrev_permute_tiled<<<grid, dim3(32, 8), 0, st>>>(in + j0 * in_stride, in_stride, out + j0 * out_stride, out_stride, lg_n, scale);
+        } else {
+            dim3 grid((unsigned)((n + 255) / 256), (unsigned)wj);
+            k_bitrev_permute<<<grid, 256, 0, st>>>(in + j0 * in_stride, in_stride, out + j0 * out_stride, out_stride, lg_n, scale);
+        }
     }
     return cudaGetLastError();
 }
@@ -625,20 +654,58 @@ cudaError_t launch_gather_rows(const uint64_t* cols, size_t col_stride, uint32_t
     return cudaGetLastError();
 }
 
-// data[j][i] *= base^i   (coset_ifft: coefficients of P(shift x) -> coefficients of P, base = shift^-1)
-__global__ void k_mul_powers(uint64_t* data, size_t stride, size_t n, uint64_t base) {
+// data[j][i] *= base^i   (coset_ifft: coefficients of P(shift x) -> coefficients of P, base = shift^-1; polynomial/mod.rs:68-72)
+// base^i = hi[i >> 10] * lo[i & 1023] from two small tables (n / 1024 + 1024 exponentiations in all) instead of one
+// exponentiation per element: two multiplications per element, HBM bound.
+__global__ void k_power_tables(uint64_t base, size_t n, uint64_t* lo, uint64_t* hi) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 1024) lo[i] = gl::pow(base, i);
+    size_t n_hi = (n + 1023) >> 10;
+    if (i < n_hi) hi[i] = gl::pow(base, i << 10);
+}
+
+__global__ void k_mul_powers(uint64_t* data, size_t stride, size_t n, const uint64_t* __restrict__ lo,
+                             const uint64_t* __restrict__ hi) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t* p = data + blockIdx.y * stride + i;
-    *p = gl::canon(gl::mul(*p, gl::pow(base, i)));
+    *p = gl::canon(gl::mul(gl::mul(*p, lo[i & 1023]), hi[i >> 10]));
 }
 
 cudaError_t launch_mul_powers(uint64_t* data, size_t stride, size_t w, size_t n, uint64_t base, cudaStream_t st) {
     if (w == 0 || n == 0) return cudaSuccess;
+    const size_t n_hi = (n + 1023) >> 10;
+    uint64_t* tab = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&tab, (1024 + n_hi) * 8, st);
+    if (e != cudaSuccess) return e;
+    const size_t nt = n_hi > 1024 ? n_hi : 1024;
+    k_power_tables<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(base % gl::P, n, tab, tab + 1024);
     for (size_t j0 = 0; j0 < w; j0 += 65535) {
         size_t wj = w - j0 < 65535 ? w - j0 : 65535;
-        k_mul_powers<<<dim3((unsigned)((n + 255) / 256), (unsigned)wj), 256, 0, st>>>(data + j0 * stride, stride, n, base);
+        k_mul_powers<<<dim3((unsigned)((n + 255) / 256), (unsigned)wj), 256, 0, st>>>(data + j0 * stride, stride, n, tab, tab + 1024);
     }
+    e = cudaGetLastError();
+    cudaFreeAsync(tab, st);
+    return e;
+}
+
+// rows in NATURAL LDE order with a stride: out[k][j] = cols[j][brev_{lg_n}((index_start + k) * step)], k < count, j < width --
+// what get_lde_values(index_start + k, step) returns (oracle.rs:128-133), for a whole range of points at once.  Writes are
+// coalesced (a warp writes one 256-byte piece of a row); reads are one sector per element (bit-reversed order has no locality).
+__global__ void __launch_bounds__(256) k_lde_natural(const uint64_t* __restrict__ cols, size_t col_stride, uint32_t width,
+                                                    unsigned lg_n, size_t index_start, size_t step, size_t count,
+                                                    uint64_t* __restrict__ out) {
+    const size_t k = (size_t)blockIdx.x * 8 + threadIdx.y;
+    if (k >= count) return;
+    const size_t idx = (index_start + k) * step;
+    const size_t leaf = lg_n ? (size_t)(__brevll((unsigned long long)idx) >> (64 - lg_n)) : 0;
+    for (uint32_t j = threadIdx.x; j < width; j += 32) out[k * width + j] = __ldg(cols + (size_t)j * col_stride + leaf);
+}
+
+cudaError_t launch_lde_natural(const uint64_t* cols, size_t col_stride, uint32_t width, unsigned lg_n, size_t index_start,
+                               size_t step, size_t count, uint64_t* out, cudaStream_t st) {
+    if (count == 0 || width == 0) return cudaSuccess;
+    k_lde_natural<<<(unsigned)((count + 7) / 8), dim3(32, 8), 0, st>>>(cols, col_stride, width, lg_n, index_start, step, count, out);
     return cudaGetLastError();
 }
 

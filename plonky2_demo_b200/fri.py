@@ -302,6 +302,13 @@ class PolynomialBatch:
             rows = rows[:, : rows.shape[1] - SALT_SIZE]
         return np.ascontiguousarray(rows.T)
 
+    def lde_values_natural(self, index_start, step, count):
+        """get_lde_values(index_start + k, step) for k < count in one device call: [count][n_polys] (salts dropped) -- the rows
+        compute_quotient_polys walks (plonk/prover.rs:576-744), prefetched in bulk instead of 32 points at a time."""
+        out = np.empty((count, self.n_polys), dtype=np.uint64)
+        _ffi.check(_ffi.lib().pcs_batch_lde_natural(self._h, index_start, step, count, _ffi.ptr(out)))
+        return out
+
     def timings(self):
         ms = (C.c_float * 5)()
         _ffi.check(_ffi.lib().pcs_batch_timings(self._h, ms))

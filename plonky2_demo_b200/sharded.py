@@ -71,10 +71,33 @@ class ShardPlan:
         self.n_leaves = 1 << (lg_d + rate_bits)
         self.local_leaves = self.n_leaves >> lg_w
         self.w_max = -(-w // world)                           # block distribution of polynomials
-        # streaming exchange: the polynomials are cut into `chunks` contiguous groups and EVERY group is block-
-        # distributed over the ranks, so that group c can be gathered (and extended) while group c+1 is still moving
-        self.chunks = max(1, min(int(chunks), w))
-        self.w_chunk = -(-w // self.chunks)
+        # streaming exchange: the polynomials are cut into contiguous groups and EVERY group is block-distributed over the
+        # ranks, so that group c can be gathered, extended AND hashed (streaming sponge: group boundaries are multiples of the
+        # sponge rate 8) while group c+1 is still moving.  `chunks` = a count (first group small -- it is the only transfer
+        # nothing hides --, the rest in equal multiples of 8) or an explicit list of group sizes.
+        if isinstance(chunks, (list, tuple)):
+            sizes = [int(x) for x in chunks if int(x) > 0]
+            if sum(sizes) != w:
+                raise ValueError(f"chunk sizes {sizes} must add up to {w} polynomials")
+        else:
+            k = max(1, min(int(chunks), w))
+            if k == 1 or w <= 16:
+                k = min(k, w)
+                base = -(-w // k)
+                sizes = [min(base, w - i * base) for i in range(k) if w - i * base > 0]
+            else:
+                first = 8
+                per = -(-(w - first) // (k - 1))
+                per = -(-per // 8) * 8
+                sizes, left = [first], w - first
+                while left > 0:
+                    sizes.append(min(per, left))
+                    left -= sizes[-1]
+        self.bounds = [0]
+        for x in sizes:
+            self.bounds.append(self.bounds[-1] + x)
+        self.chunks = len(sizes)
+        self.w_chunk = max(sizes)
 
     def coset_first(self, rank):
         if not self.coset_partition:
@@ -94,8 +117,7 @@ class ShardPlan:
         return lo, min(lo + self.w_max, self.w)
 
     def chunk_range(self, c):
-        lo = min(c * self.w_chunk, self.w)
-        return lo, min(lo + self.w_chunk, self.w)
+        return self.bounds[c], self.bounds[c + 1]
 
     def chunk_rows(self, c):
         """rows per rank in the gather of chunk c (padded)"""

@@ -11,6 +11,7 @@ Rust Vecs), checks caps against the CPU oracle and prints GPU vs CPU-port wall t
 
     python tests/harness/demo_shapes.py            # needs a B200
 """
+import ctypes as C
 import json
 import os
 import statistics
@@ -102,6 +103,58 @@ def opening_proof(m, lg_d):
     return rec
 
 
+def quotient_phase(m, lg_d, r=3, quotient_degree_bits=3):
+    """what compute_quotient_polys (plonk/prover.rs:576-744) asks of the committed batches when they are
+    device-resident.  It walks all degree * 2^quotient_degree_bits points in batches of 32 (:574,615), per batch one
+    get_lde_values_packed per oracle (constants+sigmas, wires, Z / partial products; oracle.rs:137-159), and ends with one
+    coset_ifft per challenge (:739-743).  Measured: (a) ONE bulk pcs_batch_lde_natural per oracle (rows land in host memory in
+    the order the loop walks them), (b) the per-batch-of-32 synchronous form, extrapolated from 64 calls, (c) the coset_ifft of
+    the 2 quotient polynomials through the host entry point and on the device."""
+    import torch
+
+    from plonky2_demo_b200 import _ffi
+
+    step = 1 << (r - quotient_degree_bits)
+    n_points = (1 << lg_d) << quotient_degree_bits
+    rec = {"points": n_points, "step": step, "oracles": []}
+    for name, w, _ in COMMITS[:3]:
+        x = seeded_polys(w, 1 << lg_d, base_seed=3000 * m + w)
+        b = pcs.PolynomialBatch.from_coeffs(x, r, False, 4)
+        bulk = med(lambda: b.lde_values_natural(0, step, n_points), 3)
+        rows = b.lde_values_natural(0, step, n_points)
+        ok = np.array_equal(rows[:64], np.stack([b.get_lde_values(i, step) for i in range(64)]))
+        calls = min(64, n_points // 32)
+        t0 = time.perf_counter()
+        for k in range(calls):
+            b.get_lde_values_packed(32 * k, step, 32)
+        per_call = 1e3 * (time.perf_counter() - t0) / calls
+        rec["oracles"].append({"name": name, "polys": w, "bulk_rows_ms": bulk, "bulk_GBps": n_points * w * 8 / (bulk * 1e-3) / 1e9,
+                               "rows_equal_get_lde_values": bool(ok), "per_32_points_call_ms": per_call,
+                               "per_32_points_total_ms_extrapolated": per_call * (n_points // 32)})
+        b.free()
+    lg_q = lg_d + quotient_degree_bits
+    vals = seeded_polys(2, 1 << lg_q, base_seed=99 + m)
+    want = None
+    def host():
+        v = vals.copy()
+        _ffi.check(_ffi.lib().pcs_coset_intt(_ffi.ptr(v), 2, lg_q, 7))
+        return v
+    want = host()
+    t = torch.from_numpy(vals.view(np.int64).copy()).cuda()
+    def dev():
+        t2 = t.clone()
+        _ffi.check(_ffi.lib().pcs_coset_intt_dev(C.c_void_p(t2.data_ptr()), 2, lg_q, 7))
+        _ffi.check(_ffi.lib().pcs_synchronize())
+        return t2
+    same = np.array_equal(dev().cpu().numpy().view(np.uint64), want)
+    cpu_ms = med(lambda: oracle.fft(vals, inverse=True), 3)
+    rec["coset_ifft"] = {"polys": 2, "lg_n": lg_q, "host_entry_ms": med(host, 5), "device_entry_ms": med(dev, 5), "device_equals_host": bool(same),
+                         "cpu_port_ifft_ms": cpu_ms}
+    rec["bulk_rows_ms_total"] = sum(o["bulk_rows_ms"] for o in rec["oracles"])
+    rec["per_32_points_ms_total_extrapolated"] = sum(o["per_32_points_total_ms_extrapolated"] for o in rec["oracles"])
+    return rec
+
+
 def main():
     pcs.init(0)
     out = {"rate_bits": 3, "cap_height": 4, "cpu_threads": oracle.num_threads(), "configs": []}
@@ -130,6 +183,7 @@ def main():
                                            "gpu_ms": med(lambda: pcs.MerkleTree.new(leaves, 4)),
                                            "cpu_port_ms": med(lambda: oracle.merkle_build(leaves, 4), 3)})
         rec["opening_proof"] = opening_proof(m, lg_d)
+        rec["quotient_phase"] = quotient_phase(m, lg_d)
         rec["gpu_ms_total"] = sum(c["gpu_ms"] for c in rec["commits"]) + sum(c["gpu_ms"] for c in rec["fri_layer_trees"])
         rec["cpu_port_ms_total"] = sum(c["cpu_port_ms"] for c in rec["commits"]) + sum(c["cpu_port_ms"] for c in rec["fri_layer_trees"])
         out["configs"].append(rec)

@@ -217,3 +217,34 @@ def test_c_abi_smoke_links_with_gcc_and_fails_loudly_without_a_gpu(tmp_path):
     r = subprocess.run([exe, "1", "4"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 2
     assert "no CPU fallback" in r.stderr
+
+
+def test_rust_shim_patches_apply_to_the_reference(tmp_path):
+    """rust/plonky2-gpu-shim/patches/*.patch must apply cleanly to the reference's files (checked where /root/reference exists,
+    i.e. in the build container; the GPU box has no reference tree), and gpu.rs may only call symbols the generated pcs-sys
+    binding declares."""
+    import shutil
+
+    shim = os.path.join(ROOT, "rust", "plonky2-gpu-shim")
+    with open(os.path.join(shim, "src", "gpu.rs")) as f:
+        gpu = f.read()
+    with open(os.path.join(ROOT, "rust", "pcs-sys", "src", "lib.rs")) as f:
+        sys_rs = f.read()
+    used = set(re.findall(r"sys::(pcs_[a-z0-9_]+)\s*\(", gpu))
+    declared = set(re.findall(r"pub fn (pcs_[a-z0-9_]+)\s*\(", sys_rs))
+    assert used and used <= declared, used - declared
+    assert set(re.findall(r"sys::(PCS_[A-Z_]+)", gpu)) <= set(re.findall(r"pub const (PCS_[A-Z_0-9]+)", sys_rs))
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "plonky2", "src", "fri")):
+        pytest.skip("no reference tree on this machine")
+    patches = sorted(p for p in os.listdir(os.path.join(shim, "patches")) if p.endswith(".patch"))
+    assert len(patches) == 5
+    for p in patches:
+        with open(os.path.join(shim, "patches", p)) as f:
+            target = f.readline().split()[1][2:]          # "--- a/<path>"
+        dst = tmp_path / target
+        dst.parent.mkdir(parents=True, exist_ok=True)
+        shutil.copy(os.path.join(ref, target), dst)
+        r = subprocess.run(["patch", "-p1", "--forward", "-i", os.path.join(shim, "patches", p)], cwd=tmp_path, capture_output=True, text=True)
+        assert r.returncode == 0, (p, r.stdout, r.stderr)
+        assert 'feature = "cuda"' in dst.read_text() or "cuda =" in dst.read_text()

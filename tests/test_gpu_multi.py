@@ -357,3 +357,75 @@ def test_c_abi_smoke_binary(tmp_path, lg_d):
     assert r.returncode == 0, (r.stdout, r.stderr)
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["c_abi_smoke"] is True and out["multi_devices"] == n_dev, out
+
+
+# ---------------------------------------------------------------------------------------------
+# the consumers of a committed batch in compute_quotient_polys (plonk/prover.rs:576-744)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,lg_d,r,blinding", [(135, 10, 3, False), (20, 12, 3, True), (7, 5, 1, False), (3, 3, 2, True)])
+def test_lde_natural_matches_get_lde_values(pcs, w, lg_d, r, blinding):
+    """pcs_batch_lde_natural == get_lde_values(index, step) row by row (oracle.rs:128-133), for every step the prover uses
+    (step = 2^(rate_bits - quotient_degree_bits)) and for windows of the domain"""
+    d, n = 1 << lg_d, 1 << (lg_d + r)
+    coeffs = seeded_polys(w, d, base_seed=0x1DE)
+    salts = seeded_polys(4, n, base_seed=0x5A) if blinding else None
+    ref = oracle.commit_from_coeffs(coeffs, r, 0, salts=salts)
+    b = pcs.PolynomialBatch.from_coeffs(coeffs, r, blinding, 0, salts=salts)
+    lg_n = lg_d + r
+    for s in range(r + 1):
+        step = 1 << s
+        m = n // step
+        want = ref["leaves"][[brev(k * step, lg_n) for k in range(m)]][:, :w]
+        assert np.array_equal(b.lde_values_natural(0, step, m), want)
+        # a window in the middle, and the packed accessor's 32-point batches
+        lo, cnt = m // 3, min(37, m - m // 3)
+        assert np.array_equal(b.lde_values_natural(lo, step, cnt), want[lo:lo + cnt])
+        assert np.array_equal(b.get_lde_values(5 % m, step), want[5 % m])
+    from plonky2_demo_b200 import _ffi
+
+    out = np.empty((2, w), dtype=np.uint64)
+    assert _ffi.lib().pcs_batch_lde_natural(b._h, n - 1, 1, 2, _ffi.ptr(out)) != 0      # past the end of the domain
+    assert _ffi.lib().pcs_batch_lde_natural(b._h, 0, 3, 1, _ffi.ptr(out)) != 0          # step must be a power of two
+    b.free()
+
+
+def test_lde_natural_streams_large_tables(pcs):
+    """more than one 16 MB piece: the pinned double buffering must not reorder or drop rows"""
+    w, lg_d, r = 135, 14, 3
+    coeffs = seeded_polys(w, 1 << lg_d, base_seed=0xB16)
+    b = pcs.PolynomialBatch.from_coeffs(coeffs, r, False, 4)
+    n = 1 << (lg_d + r)
+    got = b.lde_values_natural(0, 1, n)                      # 141 MB
+    rng = np.random.default_rng(3)
+    idx = rng.integers(0, n, size=64)
+    rows = b.get_rows([brev(int(k), lg_d + r) for k in idx])
+    assert np.array_equal(got[idx], rows)
+    # natural order: row k is P_j(7 * w^k); check a few against direct evaluation
+    wN = oracle.primitive_root_of_unity(lg_d + r)
+    for k in (0, 1, int(idx[0])):
+        x = 7 * pow(wN, k, P) % P
+        assert int(got[k][3]) == oracle.poly_eval(coeffs[3], x)
+    b.free()
+
+
+@pytest.mark.parametrize("w,lg_n", [(16, 15), (3, 4), (1, 0), (5, 11)])
+def test_coset_intt_dev_matches_host_entry_point(pcs, w, lg_n):
+    """pcs_coset_intt_dev (device pointer, asynchronous) == pcs_coset_intt == the oracle's coset_ifft; both use the
+    table-driven shift^-i scaling and the tiled bit-reversal"""
+    import torch
+
+    from plonky2_demo_b200 import _ffi
+
+    n = 1 << lg_n
+    coeffs = seeded_polys(w, n, base_seed=0xC05E7)
+    shift = 7
+    pw = np.array([pow(shift, i, P) for i in range(n)], dtype=object)
+    scaled = np.array([[int(c) * int(p) % P for c, p in zip(row, pw)] for row in coeffs], dtype=np.uint64)
+    vals = oracle.fft(scaled)                                # values of P on shift * <w_n>
+    t = torch.from_numpy(vals.view(np.int64).copy()).cuda()
+    _ffi.check(_ffi.lib().pcs_coset_intt_dev(C.c_void_p(t.data_ptr()), w, lg_n, shift))
+    _ffi.check(_ffi.lib().pcs_synchronize())
+    assert np.array_equal(t.cpu().numpy().view(np.uint64), coeffs)
+    host = vals.copy()
+    _ffi.check(_ffi.lib().pcs_coset_intt(_ffi.ptr(host), w, lg_n, shift))
+    assert np.array_equal(host, coeffs)

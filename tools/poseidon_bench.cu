@@ -3,6 +3,7 @@
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I plonky2_demo_b200/csrc -o pb tools/poseidon_bench.cu
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "poseidon.cuh"
 
@@ -28,8 +29,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k(uint64_t* io, size_t n, 
 }
 
 int main(int argc, char** argv) {
-    size_t n = (size_t)1 << 21;
-    int reps = 17;
+    size_t n = argc > 2 ? (size_t)atol(argv[2]) : (size_t)1 << 21;   // 32 = one warp: the latency of a permutation chain
+    int reps = argc > 3 ? atoi(argv[3]) : 17;
     uint64_t* d;
     cudaMalloc(&d, n * 12 * 8);
     cudaMemset(d, 1, n * 12 * 8);
