@@ -79,11 +79,13 @@ def parse():
     ap.add_argument("--no-multi-in-process", action="store_true", help="N > 1: skip the pcs_multi_* (one process, N GPUs) timing")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fri", action="store_true", help="skip the opening-proof (FRI) timings")
-    ap.add_argument("--chunks", type=int, default=4,
-                    help="N > 1: polynomial groups of the streaming exchange (1 = one all-gather, then the LDE)")
-    ap.add_argument("--e2e-chunks", type=int, default=5,
-                    help="N > 1: polynomial groups of the streaming exchange in the END-TO-END arm, where every chunk also crosses "
-                         "PCIe first: more, smaller chunks expose less of the first copy (2 GPUs: 68.4 ms with 4 against 70.4 ms with 2)")
+    ap.add_argument("--chunks", default="3",
+                    help="N > 1: polynomial groups of the streaming exchange in the device-resident arm: a count (first group 8 "
+                         "polynomials, the rest equal) or host:<rho> (1 = one all-gather, then the LDE)")
+    ap.add_argument("--e2e-chunks", default="auto",
+                    help="N > 1: groups of the END-TO-END arm, where every group also crosses PCIe first.  auto = host:<rho> with "
+                         "rho = transfer / compute time per polynomial (0.75 at N >= 4 where the host side saturates, 0.4 at N = 2): "
+                         "geometrically growing groups, only the first 8-polynomial transfer is exposed")
     ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer"],
                     help="N > 1: how coefficient blocks reach the other ranks (plonky2_demo_b200/sharded.py)")
     return ap.parse_args()
@@ -402,7 +404,7 @@ def large_commit_bench(a, world, rank, dev, stream, lg_d=24):
 
     w, r, cap_h = a.width, a.rate_bits, a.cap_height
     d = 1 << lg_d
-    plan = ShardPlan(w, lg_d, r, cap_h, world, a.chunks)
+    plan = ShardPlan(w, lg_d, r, cap_h, world, int(a.chunks) if str(a.chunks).isdigit() else a.chunks)
     mine = plan.local_polys(rank)
     t0 = time.perf_counter()
     host = np.empty((len(mine), d), dtype=np.uint64)
@@ -418,7 +420,7 @@ def large_commit_bench(a, world, rank, dev, stream, lg_d=24):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        batch = ShardedPolynomialBatch.from_coeffs(local, w, r, cap_h, partitioned=True, exchange=a.exchange, chunks=plan.chunks)
+        batch = ShardedPolynomialBatch.from_coeffs(local, w, r, cap_h, partitioned=True, exchange=a.exchange, chunks=plan.sizes)
         e1.record(stream)
         dist.barrier()
         torch.cuda.synchronize()
@@ -488,7 +490,9 @@ def run_ours(a):
     # polynomials; world > 1: this rank's block of the same W polynomials (plonky2_demo_b200/sharded.py)
     from plonky2_demo_b200.sharded import ShardedPolynomialBatch, ShardPlan
 
-    chunks = a.chunks if a.exchange != "peer" else 1
+    def chunk_spec(x):
+        return int(x) if str(x).isdigit() else x
+    chunks = chunk_spec(a.chunks) if a.exchange != "peer" else 1
     plan = ShardPlan(w, lg_d, r, cap_h, world, chunks if world > 1 else 1)
     my_polys = plan.local_polys(rank) if world > 1 else list(range(w))
     w_loc = len(my_polys)
@@ -499,9 +503,10 @@ def run_ours(a):
         host_np[j] = splitmix64_stream(0x5EED0000 + pj, d)
     dev_coeffs = host.to(dev, non_blocking=False)
     # end-to-end arm: its own chunking (and therefore its own block distribution of the same W polynomials)
-    e2e_chunks = a.e2e_chunks if (a.exchange != "peer" and world > 1) else plan.chunks
+    e2e_spec = a.e2e_chunks if a.e2e_chunks != "auto" else f"host:{0.75 if world >= 4 else 0.4}"
+    e2e_chunks = chunk_spec(e2e_spec) if (a.exchange != "peer" and world > 1) else plan.sizes
     plan_e2e = ShardPlan(w, lg_d, r, cap_h, world, e2e_chunks if world > 1 else 1)
-    if world > 1 and plan_e2e.chunks != plan.chunks and not a.no_e2e:
+    if world > 1 and plan_e2e.sizes != plan.sizes and not a.no_e2e:
         polys_e2e = plan_e2e.local_polys(rank)
         host_e2e = torch.empty((len(polys_e2e), d), dtype=torch.int64, pin_memory=True)
         he = host_e2e.numpy().view(np.uint64)
@@ -532,7 +537,7 @@ def run_ours(a):
     def commit_device():
         if world > 1:
             return _Sharded(ShardedPolynomialBatch.from_coeffs(dev_coeffs, w, r, cap_h, partitioned=True, exchange=a.exchange,
-                                                               chunks=plan.chunks))
+                                                               chunks=plan.sizes))
         h = C.c_void_p()
         _ffi.check(L.pcs_commit_from_coeffs(dev_ptrs, w, lg_d, r, cap_h, None, 0, _ffi.PCS_DEVICE_PTRS, None, C.byref(h)))
         return h
@@ -541,7 +546,7 @@ def run_ours(a):
         if world > 1:
             # streaming exchange: the pinned host block goes in as it is, chunk c+1 crosses PCIe / NVLink under the LDE of chunk c
             src = host_e2e if plan_e2e.chunks > 1 else host_e2e.to(dev, non_blocking=True)
-            b = ShardedPolynomialBatch.from_coeffs(src, w, r, cap_h, partitioned=True, exchange=a.exchange, chunks=plan_e2e.chunks)
+            b = ShardedPolynomialBatch.from_coeffs(src, w, r, cap_h, partitioned=True, exchange=a.exchange, chunks=plan_e2e.sizes)
             cap_host[:] = b.cap
             return _Sharded(b)
         h = C.c_void_p()
@@ -660,7 +665,7 @@ def run_ours(a):
         assert np.array_equal(cap_host, cap_dev), "host-path and device-path caps differ"
         e2e = {"value": elems * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(host_e2e.shape[0]) * d * 8, "d2h_bytes_per_step": (1 << cap_h) * 32,
-               "exchange_chunks": plan_e2e.chunks if world > 1 else None,
+               "exchange_chunks": plan_e2e.sizes if world > 1 else None,
                "ms_per_step": e2e_ms / a.steps,
                "note": "pinned host coefficients -> pcs_commit_from_coeffs (host pointers) -> Merkle cap on host; "
                        "LDE rows and digests stay device-resident behind the batch handle"}
@@ -752,11 +757,11 @@ def run_ours(a):
             b.free()
     else:
         # (i) the SHARDED path (real NCCL exchange, streaming chunks) against the CPU oracle at the sample size
-        plan_s = ShardPlan(w, lg_s, r, cap_h, world, plan.chunks)
+        plan_s = ShardPlan(w, lg_s, r, cap_h, world, plan.sizes)
         mine_s = plan_s.local_polys(rank)
         loc = np.stack([splitmix64_stream(0x5EED0000 + pj, 1 << lg_s) for pj in mine_s]) if mine_s else np.empty((0, 1 << lg_s), np.uint64)
         bs = ShardedPolynomialBatch.from_coeffs(torch.from_numpy(loc.view(np.int64)).to(dev), w, r, cap_h, partitioned=True,
-                                                exchange=a.exchange, chunks=plan_s.chunks)
+                                                exchange=a.exchange, chunks=plan_s.sizes)
         cap_s = np.array(bs.cap)
         leaf_s = (1 << (lg_s + r)) - 5
         row_s = bs.get_rows([leaf_s])[0]
@@ -790,8 +795,16 @@ def run_ours(a):
     if world > 1 and not a.no_multi_in_process:
         dist.barrier()
         torch.cuda.synchronize()
+        # the other ranks wait on the rendezvous STORE (a host-side wait): an NCCL barrier would leave a spinning kernel on their
+        # GPUs, and kernels of two processes time-slice a GPU
+        store = dist.distributed_c10d._get_default_store()
         if rank == 0:
-            out["kernels"]["multi_in_process"] = multi_in_process_bench(a, world, cap_dev)
+            try:
+                out["kernels"]["multi_in_process"] = multi_in_process_bench(a, world, cap_dev)
+            finally:
+                store.set("pcs_multi_in_process_done", "1")
+        else:
+            store.wait(["pcs_multi_in_process_done"])
         dist.barrier()
 
     # ---- BASELINE configs[4]: one 135 x 2^24 commitment over the whole box ----

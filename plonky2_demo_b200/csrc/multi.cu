@@ -51,7 +51,7 @@ struct Multi {
 Multi g_multi;
 std::recursive_mutex g_multi_mutex;   // one multi commit at a time (recursive: a failing commit frees its batch under the lock)
 
-constexpr size_t MULTI_MAX_CHUNKS = 8;
+constexpr size_t MULTI_MAX_CHUNKS = 16;
 
 uint64_t* block_take(int gi, size_t bytes) {
     auto& fl = g_multi.free_blocks[gi];
@@ -83,17 +83,24 @@ struct Plan {
     size_t chunks;
     size_t w;
     std::vector<size_t> bounds;   // chunk c = polynomials [bounds[c], bounds[c+1])
-    // Groups for the streaming pipeline: the first one small (its transfer is the only one nothing hides), the rest equal
-    // multiples of the sponge rate 8 so that every group can be hashed as soon as it is extended.
-    void make_chunks(size_t k) {
+    // Groups for the streaming pipeline.  The H2D copies run back to back on the copy stream; a group boundary only decides
+    // when compute may start on what has arrived.  With t = transfer time and c = compute time per polynomial (rho = t / c < 1),
+    // group k+1 has landed before group k is finished iff  b[k+2] <= b[1] + b[k+1] / rho  (b = cumulative bounds), so the
+    // groups may grow geometrically and only the FIRST transfer (8 polynomials = one sponge absorb) is exposed.  Boundaries are
+    // multiples of the sponge rate 8 so that every group is hashed as soon as it is extended.
+    void make_chunks(double rho) {
         bounds.assign(1, 0);
-        if (k <= 1 || w <= 16) {
+        if (rho <= 0 || w <= 16) {
             bounds.push_back(w);
         } else {
-            size_t per = (w - 8 + (k - 2)) / (k - 1);
-            per = (per + 7) / 8 * 8;
             bounds.push_back(8);
-            while (bounds.back() < w) bounds.push_back(bounds.back() + per < w ? bounds.back() + per : w);
+            while (bounds.back() < w && bounds.size() < MULTI_MAX_CHUNKS) {
+                size_t next = (size_t)(8 + bounds.back() / rho) / 8 * 8;
+                if (next <= bounds.back()) next = bounds.back() + 8;
+                bounds.push_back(next < w ? next : w);
+            }
+            if (bounds.back() < w) bounds.back() = w;
+            if (bounds.size() > 2 && w - bounds[bounds.size() - 2] < 8) bounds.erase(bounds.end() - 2);
         }
         chunks = bounds.size() - 1;
     }
@@ -265,13 +272,12 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
     const size_t d = (size_t)1 << lg_d, n = d << rate_bits, n_loc = n >> plan.lg_dev;
     // device-resident inputs are read in place; host inputs arrive in chunks (H2D of chunk c+1 under the LDE of chunk c)
     const bool staged = !dev_ptrs || from_values;   // from_values transforms in place: always on engine-owned blocks
-    size_t want_chunks = 1;
-    if (staged && !from_values && !dev_ptrs) {
-        size_t by_size = (w * d * 8) >> 23;          // ~8 MB per device and chunk at least
-        want_chunks = by_size / G < 1 ? 1 : by_size / G;
-        if (want_chunks > MULTI_MAX_CHUNKS - 2) want_chunks = MULTI_MAX_CHUNKS - 2;
-    }
-    plan.make_chunks(want_chunks);
+    // host inputs: pipeline the H2D copies under the compute.  rho = transfer / compute time per polynomial: one device moves a
+    // polynomial in ~0.15 ms against ~0.9 ms of LDE + hashing (2^20, rate 3); with 8 devices copying at once the host side
+    // saturates and the ratio approaches 0.75 (profiles/r02_scaling.md)
+    double rho = 0;
+    if (staged && !from_values && !dev_ptrs && w * d * 8 >= ((size_t)G << 24)) rho = G >= 4 ? 0.75 : (G == 2 ? 0.4 : 0.25);
+    plan.make_chunks(rho);
     if (plan.chunks > MULTI_MAX_CHUNKS) return fail(PCS_ERR_ARG, "internal: too many chunks");
     const size_t n_local_cap = (size_t)1 << plan.local_cap_height;
 

@@ -75,6 +75,18 @@ class ShardPlan:
         # ranks, so that group c can be gathered, extended AND hashed (streaming sponge: group boundaries are multiples of the
         # sponge rate 8) while group c+1 is still moving.  `chunks` = a count (first group small -- it is the only transfer
         # nothing hides --, the rest in equal multiples of 8) or an explicit list of group sizes.
+        if isinstance(chunks, str):
+            # "host:<rho>": inputs stream from pinned host memory; rho = transfer time / compute time per polynomial.  The copies
+            # run back to back, so group k+1 has landed before group k is finished iff b[k+2] <= b[1] + b[k+1] / rho: the
+            # groups grow geometrically and only the first transfer (8 polynomials) is exposed.
+            rho = float(chunks.split(":")[1]) if ":" in chunks else 0.75
+            b = [0, min(8, w)]
+            while b[-1] < w:
+                nxt = int(8 + b[-1] / rho) // 8 * 8
+                b.append(min(max(nxt, b[-1] + 8), w))
+            if len(b) > 2 and w - b[-2] < 8:
+                del b[-2]
+            chunks = [hi - lo for lo, hi in zip(b, b[1:])]
         if isinstance(chunks, (list, tuple)):
             sizes = [int(x) for x in chunks if int(x) > 0]
             if sum(sizes) != w:
@@ -97,6 +109,7 @@ class ShardPlan:
         for x in sizes:
             self.bounds.append(self.bounds[-1] + x)
         self.chunks = len(sizes)
+        self.sizes = sizes
         self.w_chunk = max(sizes)
 
     def coset_first(self, rank):
@@ -301,6 +314,16 @@ class CudaShardEngine:
         self._order_after_torch()
         _ffi.check(_ffi.lib().pcs_shard_finish(handle, _ffi.ptr(cap)))
         return cap
+
+    def shard_finish_dev(self, handle, plan):
+        """pcs_shard_finish without the host round trip: the local cap stays on the device (torch view) for the cap all-gather"""
+        import torch
+
+        self._order_after_torch()
+        _ffi.check(_ffi.lib().pcs_shard_finish(handle, None))
+        self._order_torch_after_engine()
+        base = _ffi.lib().pcs_batch_cap_dev(handle)
+        return torch.as_tensor(_DeviceView(base, plan.local_cap_len() * 4), device="cuda").view(-1, 4)
 
     def two_to_one(self, left, right):
         from .hashing import PoseidonHash
@@ -553,7 +576,10 @@ class ShardedPolynomialBatch:
             engine.shard_extend(self._h, clo, gathered[c][0], chi - clo)
         if salt_rows is not None:
             engine.set_rows(self._h, plan.w, engine.to_device(salt_rows, gathered[0][0]), False)
-        local_cap = engine.shard_finish(self._h, plan)
+        if cuda and hasattr(engine, "shard_finish_dev"):
+            local_cap = engine.shard_finish_dev(self._h, plan)      # device tensor: gathered without a host round trip
+        else:
+            local_cap = engine.shard_finish(self._h, plan)
         self._coeffs = gathered          # keeps the gathered chunks alive ([chunk][world*m][d]); polynomials of chunk c = rows [0, len_c)
         self._dev = dev
         return cls._finish_caps(self, local_cap, dev, world, group, engine,
@@ -566,11 +592,13 @@ class ShardedPolynomialBatch:
         import torch.distributed as dist
 
         if world > 1:
-            mine = torch.from_numpy(local_cap.view(np.int64)).to(dev)
+            mine = local_cap if isinstance(local_cap, torch.Tensor) else torch.from_numpy(local_cap.view(np.int64)).to(dev)
             allc = torch.empty((world * mine.shape[0], 4), dtype=torch.int64, device=dev)
             dist.all_gather_into_tensor(allc, mine, group=group)
             caps = allc.cpu().numpy().view(np.uint64).reshape(world, -1, 4)
         else:
+            if isinstance(local_cap, torch.Tensor):
+                local_cap = local_cap.cpu().numpy().view(np.uint64)
             caps = local_cap[None]
         self._local_caps = caps
         self.cap = self.plan.assemble_cap(caps, engine.two_to_one)
