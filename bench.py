@@ -694,8 +694,8 @@ def run_ours(a):
                 "clk_per_permutation_per_sm_lane": (leaf_ms * 1e-3) * sm_mhz * 1e6 * 148 / max(n_perm_leaf, 1),
                 "sm_mhz_used": sm_mhz}
     # issue-slot view of the same launch: instructions per permutation are a property of the compiled kernel (ncu
-    # smsp__inst_executed x 32 / permutations, profiles/r01_poseidon_v3.md); an SM issues 4 x 32 thread-instructions per clock
-    INSTR_PER_PERMUTATION = 16950.0
+    # smsp__inst_executed x 32 / permutations of the shipped k_hash_cols, profiles/r02_leafhash.md); an SM issues 4 x 32 thread-instructions per clock
+    INSTR_PER_PERMUTATION = 17080.0   # profiles/r02_leafhash.md: 7.611e10 warp-instructions x 32 / (17 x 2^23)
     issue_peak = 148 * 128 * sm_mhz * 1e6
     int_pipe.update({
         "thread_instr_per_permutation": INSTR_PER_PERMUTATION,
