@@ -30,6 +30,8 @@ struct Ctx {
     void* pin_in = nullptr;  size_t pin_in_bytes = 0;
     void* pin_out = nullptr; size_t pin_out_bytes = 0;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t d2h_stream = nullptr;    // coefficients going back to the host while the LDE / hashing continue
+    std::vector<cudaEvent_t> d2h_ev;
     cudaEvent_t ev_sync = nullptr;
     std::vector<cudaEvent_t> chunk_ev;
     // PAGEABLE host inputs (Rust Vecs, numpy arrays): gathered by a few host threads into a ring of pinned slots and
@@ -112,9 +114,15 @@ pcs_batch* batch_new() {
 static int node_levels_dev(size_t n, unsigned lg_sub, uint64_t* digests, uint64_t* cap, cudaStream_t st) {
     // one launch per level while a level still fills the GPU (more than 256 nodes per cap subtree), then the top of every
     // subtree in ONE launch
+    // (levels of <= 8192 nodes run in the latency form, one node per half-warp: node_hash.cu; the top launch then starts
+    // once a subtree has <= 64 nodes, before that it needs <= 256)
     unsigned level = 1;
-    for (; level <= lg_sub && lg_sub - level > 8; level++)
-        PCS_CUDA(launch_node_level(digests, cap, lg_sub, level, n >> level, st));
+    for (; level <= lg_sub; level++) {
+        const size_t nodes = n >> level;
+        const unsigned left = lg_sub - level;                     // log2(nodes per subtree at this level)
+        if (nodes <= 8192 ? left <= 6 : left <= 8) break;
+        PCS_CUDA(launch_node_level(digests, cap, lg_sub, level, nodes, st));
+    }
     if (level <= lg_sub) PCS_CUDA(launch_node_top(digests, cap, lg_sub, level, n >> lg_sub, st));
     return PCS_OK;
 }
@@ -231,6 +239,8 @@ static void ctx_destroy(Ctx* c) {
     drain_pending();
     ntt_plans_free();                  // this device's twiddle tables
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    for (auto& e : c->d2h_ev) cudaEventDestroy(e);
     if (c->pin_in) cudaFreeHost(c->pin_in);
     if (c->pin_out) cudaFreeHost(c->pin_out);
     if (c->ev_sync) cudaEventDestroy(c->ev_sync);
@@ -749,6 +759,7 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
     struct CopyDrain {
         bool armed = false;
         ~CopyDrain() {
+            if (g_ctx.d2h_stream) cudaStreamSynchronize(g_ctx.d2h_stream);   // D2H copies out of a buffer the guard is about to free
             if (!armed || !g_ctx.copy_stream) return;
             cudaStreamSynchronize(g_ctx.copy_stream);
             for (auto& busy : g_ctx.ring_busy) busy = false;
@@ -841,13 +852,32 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
     uint64_t* const ifft_scratch = b->lde + (wt * n - w * d);
     const bool small_out = from_values && coeffs_out && d * 8 <= SMALL_POLY_BYTES && w * d * 8 <= PIN_STAGING_MAX &&
                            pinned(g_ctx.pin_out, g_ctx.pin_out_bytes, w * d * 8);
+    // larger outputs (the reference keeps `polynomials`, so a Rust caller always asks for them): every chunk's coefficients
+    // leave on their own stream into pinned staging while the LDE and the hashing go on, and are scattered into the caller's
+    // (pageable, separately allocated) vectors by a few host threads after the commit
+    const bool big_out = from_values && coeffs_out && !small_out && w * d * 8 <= ((size_t)512 << 20) &&
+                         pinned(g_ctx.pin_out, g_ctx.pin_out_bytes, w * d * 8);
+    size_t n_d2h = 0;
+    if (big_out && !g_ctx.d2h_stream) PCS_CUDA(cudaStreamCreateWithFlags(&g_ctx.d2h_stream, cudaStreamNonBlocking));
     auto ifft_range = [&](size_t j0, size_t j1) -> int {
         PCS_CUDA(ntt_inverse_bitrev(iplan, src + j0 * d, d, ifft_scratch + j0 * d, d, j1 - j0, st));
         PCS_CUDA(launch_bitrev_permute(ifft_scratch + j0 * d, d, staged + j0 * d, d, j1 - j0, lg_d, st, ntt_plan_scale(iplan)));
-        if (coeffs_out && !small_out)
+        if (big_out) {
+            if (g_ctx.d2h_ev.size() <= n_d2h) {
+                cudaEvent_t e;
+                PCS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                g_ctx.d2h_ev.push_back(e);
+            }
+            PCS_CUDA(cudaEventRecord(g_ctx.d2h_ev[n_d2h], st));
+            PCS_CUDA(cudaStreamWaitEvent(g_ctx.d2h_stream, g_ctx.d2h_ev[n_d2h], 0));
+            n_d2h++;
+            PCS_CUDA(cudaMemcpyAsync((char*)g_ctx.pin_out + j0 * d * 8, staged + j0 * d, (j1 - j0) * d * 8, cudaMemcpyDeviceToHost,
+                                     g_ctx.d2h_stream));
+        } else if (coeffs_out && !small_out) {
             for (size_t j = j0; j < j1; j++)
                 if (coeffs_out[j])
                     PCS_CUDA(cudaMemcpyAsync(coeffs_out[j], staged + j * d, d * 8, cudaMemcpyDeviceToHost, st));
+        }
         return PCS_OK;
     };
     const bool chunked = n_chunks > 0;   // host inputs arriving chunk by chunk: IFFT and LDE follow each chunk
@@ -934,6 +964,19 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
     if (scatter_coeffs)
         for (size_t j = 0; j < w; j++)
             if (coeffs_out[j]) memcpy(coeffs_out[j], (char*)g_ctx.pin_out + j * d * 8, d * 8);
+    if (big_out) {
+        PCS_CUDA(cudaStreamSynchronize(st));
+        PCS_CUDA(cudaStreamSynchronize(g_ctx.d2h_stream));
+        const unsigned nt = STAGE_THREADS;
+        std::thread th[STAGE_THREADS];
+        const char* srcp = (const char*)g_ctx.pin_out;
+        for (unsigned t = 0; t < nt; t++)
+            th[t] = std::thread([=]() {
+                for (size_t j = t; j < w; j += nt)
+                    if (coeffs_out[j]) memcpy(coeffs_out[j], srcp + j * d * 8, d * 8);
+            });
+        for (unsigned t = 0; t < nt; t++) th[t].join();
+    }
     guard.armed = false;
     copy_drain.armed = false;   // the main stream waited on every chunk event and has been synchronised (host inputs)
     b->committed = true;

@@ -8,6 +8,7 @@
 //
 // Bound: integer pipes, NOT HBM: a 135-element leaf = 17 permutations per 1080 B read.
 #include "hash_common.cuh"
+#include "poseidon_coop.cuh"
 
 namespace pcs {
 
@@ -77,6 +78,33 @@ k_hash_cols_stream(const uint64_t* __restrict__ cols, size_t col_stride, uint32_
     }
 }
 
+// Latency form for small trees (<= COOP_MAX_PERMS leaves): one LEAF per half-warp, the 12 state lanes on 12 threads.
+__global__ void __launch_bounds__(128)
+k_hash_cols_coop(const uint64_t* __restrict__ cols, size_t col_stride, uint32_t width, size_t first, size_t n, int tree_mode,
+                 unsigned lg_sub, uint64_t* __restrict__ digests, uint64_t* __restrict__ cap) {
+    __shared__ uint64_t rc[360];
+    coop_load_rc(rc);
+    const size_t leaf = first + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / COOP_LANES;
+    const unsigned i = threadIdx.x & (COOP_LANES - 1);
+    const bool active = leaf < n;                       // uniform over the half-warp; idle half-warps still run the shuffles
+    const uint64_t* p = cols + (active ? leaf : first);
+    uint64_t s = 0;
+    if (width <= 4) {                                   // hash_or_noop: not hashed
+        s = i < width ? gl::canon(p[(size_t)i * col_stride]) : 0;
+    } else {
+#pragma unroll 1
+        for (uint32_t j = 0; j < width; j += 8) {
+            if (i < 8 && j + i < width) s = __ldg(p + (size_t)(j + i) * col_stride);
+            s = poseidon12_coop(s, i, rc);
+        }
+        s = gl::canon(s);
+    }
+    if (active && i < 4) {
+        uint64_t* slot = tree_mode ? digest_slot(digests, cap, lg_sub, 0, leaf) : digests + 4 * leaf;
+        slot[i] = s;
+    }
+}
+
 cudaError_t launch_leaf_hash_group(const uint64_t* cols, size_t col_stride, uint32_t width, size_t n_leaves, bool first, bool last,
                                    uint64_t* state, unsigned lg_sub, uint64_t* digests, uint64_t* cap, cudaStream_t st) {
     if (n_leaves == 0) return cudaSuccess;
@@ -97,15 +125,22 @@ cudaError_t launch_leaf_hash_cols(const uint64_t* cols, size_t col_stride, uint3
                                   size_t first_leaf, size_t leaf_count) {
     if (leaf_count == (size_t)-1) leaf_count = n_leaves - first_leaf;
     if (leaf_count == 0) return cudaSuccess;
-    k_hash_cols<<<grid_for(leaf_count, HASH_THREADS), HASH_THREADS, 0, st>>>(cols, col_stride, width, first_leaf,
-                                                                            first_leaf + leaf_count, 1, lg_sub, digests, cap);
+    if (leaf_count <= COOP_MAX_PERMS)
+        k_hash_cols_coop<<<grid_for(leaf_count * COOP_LANES, 128), 128, 0, st>>>(cols, col_stride, width, first_leaf,
+                                                                                first_leaf + leaf_count, 1, lg_sub, digests, cap);
+    else
+        k_hash_cols<<<grid_for(leaf_count, HASH_THREADS), HASH_THREADS, 0, st>>>(cols, col_stride, width, first_leaf,
+                                                                                first_leaf + leaf_count, 1, lg_sub, digests, cap);
     return cudaGetLastError();
 }
 
 cudaError_t launch_hash_cols_plain(const uint64_t* cols, size_t col_stride, uint32_t width, size_t n,
                                    uint64_t* out, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    k_hash_cols<<<grid_for(n, HASH_THREADS), HASH_THREADS, 0, st>>>(cols, col_stride, width, 0, n, 0, 0, out, nullptr);
+    if (n <= COOP_MAX_PERMS)
+        k_hash_cols_coop<<<grid_for(n * COOP_LANES, 128), 128, 0, st>>>(cols, col_stride, width, 0, n, 0, 0, out, nullptr);
+    else
+        k_hash_cols<<<grid_for(n, HASH_THREADS), HASH_THREADS, 0, st>>>(cols, col_stride, width, 0, n, 0, 0, out, nullptr);
     return cudaGetLastError();
 }
 

@@ -5,6 +5,7 @@
 // tree level is one launch with one thread per node, writing into the reference digest layout.
 // prove(): merkle_tree.rs:173-207.
 #include "hash_common.cuh"
+#include "poseidon_coop.cuh"
 
 namespace pcs {
 
@@ -65,10 +66,68 @@ k_compress_top(uint64_t* __restrict__ digests, uint64_t* __restrict__ cap, unsig
     }
 }
 
+// Latency forms (<= COOP_MAX_PERMS nodes in a level): one NODE per half-warp.
+// compress of (l, r): lanes 0..3 hold l, lanes 4..7 hold r, the rest 0 (hashing.rs:98-115)
+__device__ __forceinline__ uint64_t coop_compress(const uint64_t* l, const uint64_t* r, unsigned i, const uint64_t* rc) {
+    uint64_t s = i < 4 ? l[i] : (i < 8 ? r[i - 4] : 0);
+    return gl::canon(poseidon12_coop(s, i, rc));
+}
+
+__global__ void __launch_bounds__(128)
+k_compress_coop(uint64_t* __restrict__ a, uint64_t* __restrict__ b, uint64_t* __restrict__ c, int tree_mode, unsigned lg_sub,
+                unsigned level, size_t n) {
+    __shared__ uint64_t rc[360];
+    coop_load_rc(rc);
+    const size_t k0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / COOP_LANES;
+    const unsigned i = threadIdx.x & (COOP_LANES - 1);
+    const bool active = k0 < n;
+    const size_t k = active ? k0 : 0;
+    const uint64_t *l, *r;
+    uint64_t* out;
+    if (tree_mode) {
+        l = digest_slot(a, b, lg_sub, level - 1, 2 * k);
+        r = l + 4;
+        out = digest_slot(a, b, lg_sub, level, k);
+    } else {
+        l = a + 4 * k;
+        r = b + 4 * k;
+        out = c + 4 * k;
+    }
+    const uint64_t s = coop_compress(l, r, i, rc);
+    if (active && i < 4) out[i] = s;
+}
+
+// The top of every cap subtree in one launch, latency form: levels [level_first, lg_sub], <= 64 nodes per subtree at
+// level_first, one CTA (1024 threads = 64 half-warps) per subtree.
+__global__ void __launch_bounds__(1024)
+k_compress_top_coop(uint64_t* __restrict__ digests, uint64_t* __restrict__ cap, unsigned lg_sub, unsigned level_first) {
+    __shared__ uint64_t rc[360];
+    coop_load_rc(rc);
+    const size_t sub = blockIdx.x;
+    const unsigned g = threadIdx.x / COOP_LANES, i = threadIdx.x & (COOP_LANES - 1);
+    for (unsigned level = level_first; level <= lg_sub; level++) {
+        const unsigned per = 1u << (lg_sub - level);
+        if ((g & ~1u) < per) {        // whole warps stay together: both half-warps of a warp run the shuffles
+            const bool active = g < per;
+            const size_t k = (sub << (lg_sub - level)) + (active ? g : 0);
+            const uint64_t* l = digest_slot(digests, cap, lg_sub, level - 1, 2 * k);
+            const uint64_t s = coop_compress(l, l + 4, i, rc);
+            if (active && i < 4) digest_slot(digests, cap, lg_sub, level, k)[i] = s;
+        }
+        __syncthreads();
+    }
+}
+
 cudaError_t launch_node_top(uint64_t* digests, uint64_t* cap, unsigned lg_sub, unsigned level_first, size_t n_subtrees,
                             cudaStream_t st) {
     if (n_subtrees == 0 || level_first > lg_sub) return cudaSuccess;
     if (lg_sub - level_first > 8) return cudaErrorInvalidValue;
+    if (lg_sub - level_first <= 6) {    // <= 64 nodes per subtree: the latency form
+        const unsigned nodes = 1u << (lg_sub - level_first);
+        const unsigned threads = nodes * COOP_LANES < 32 ? 32 : nodes * COOP_LANES;
+        k_compress_top_coop<<<(unsigned)n_subtrees, threads, 0, st>>>(digests, cap, lg_sub, level_first);
+        return cudaGetLastError();
+    }
     const unsigned threads = 1u << (lg_sub - level_first) < 32 ? 32 : 1u << (lg_sub - level_first);
     k_compress_top<<<(unsigned)n_subtrees, threads, 0, st>>>(digests, cap, lg_sub, level_first);
     return cudaGetLastError();
@@ -92,15 +151,20 @@ __global__ void k_prove(const uint64_t* __restrict__ digests, unsigned lg_sub, s
 cudaError_t launch_node_level(uint64_t* digests, uint64_t* cap, unsigned lg_sub, unsigned level, size_t n_nodes,
                               cudaStream_t st) {
     if (n_nodes == 0) return cudaSuccess;
-    k_compress<<<grid_for(n_nodes, HASH_THREADS), HASH_THREADS, 0, st>>>(digests, cap, nullptr, 1, lg_sub, level,
-                                                                        n_nodes);
+    if (n_nodes <= COOP_MAX_PERMS)
+        k_compress_coop<<<grid_for(n_nodes * COOP_LANES, 128), 128, 0, st>>>(digests, cap, nullptr, 1, lg_sub, level, n_nodes);
+    else
+        k_compress<<<grid_for(n_nodes, HASH_THREADS), HASH_THREADS, 0, st>>>(digests, cap, nullptr, 1, lg_sub, level, n_nodes);
     return cudaGetLastError();
 }
 
 cudaError_t launch_two_to_one(const uint64_t* l, const uint64_t* r, size_t n, uint64_t* out, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    k_compress<<<grid_for(n, HASH_THREADS), HASH_THREADS, 0, st>>>(const_cast<uint64_t*>(l), const_cast<uint64_t*>(r),
-                                                                  out, 0, 0, 0, n);
+    if (n <= COOP_MAX_PERMS)
+        k_compress_coop<<<grid_for(n * COOP_LANES, 128), 128, 0, st>>>(const_cast<uint64_t*>(l), const_cast<uint64_t*>(r), out, 0, 0, 0, n);
+    else
+        k_compress<<<grid_for(n, HASH_THREADS), HASH_THREADS, 0, st>>>(const_cast<uint64_t*>(l), const_cast<uint64_t*>(r),
+                                                                      out, 0, 0, 0, n);
     return cudaGetLastError();
 }
 

@@ -1,6 +1,7 @@
 // Batched Poseidon-12 permutation (pcs_poseidon_permute): one thread per state.
 // Reference: Poseidon::poseidon, plonky2/src/hash/poseidon.rs:599-609.
 #include "hash_common.cuh"
+#include "poseidon_coop.cuh"
 
 namespace pcs {
 
@@ -48,9 +49,25 @@ cudaError_t launch_pow_search(const uint64_t* state_dev, unsigned pos, unsigned 
     return cudaGetLastError();
 }
 
+// Latency form (<= COOP_MAX_PERMS states, e.g. the Challenger's single duplexing): one state per half-warp.
+__global__ void __launch_bounds__(128) k_permute_coop(uint64_t* __restrict__ states, size_t n) {
+    __shared__ uint64_t rc[360];
+    coop_load_rc(rc);
+    const size_t k0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / COOP_LANES;
+    const unsigned i = threadIdx.x & (COOP_LANES - 1);
+    const bool active = k0 < n;
+    uint64_t* p = states + (active ? k0 : 0) * 12;
+    uint64_t s = i < 12 ? p[i] : 0;
+    s = gl::canon(poseidon12_coop(s, i, rc));
+    if (active && i < 12) p[i] = s;
+}
+
 cudaError_t launch_permute(uint64_t* states, size_t n, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    k_permute<<<grid_for(n, HASH_THREADS), HASH_THREADS, 0, st>>>(states, n);
+    if (n <= COOP_MAX_PERMS)
+        k_permute_coop<<<grid_for(n * COOP_LANES, 128), 128, 0, st>>>(states, n);
+    else
+        k_permute<<<grid_for(n, HASH_THREADS), HASH_THREADS, 0, st>>>(states, n);
     return cudaGetLastError();
 }
 

@@ -36,8 +36,9 @@ use crate::util::log2_strict;
 use crate::util::timing::TimingTree;
 
 /// Commitments with fewer leaves than this stay on the reference's CPU path: a device commit has a fixed cost of launches and
-/// one synchronisation (include/pcs.h; DESIGN.md "small commits"), which the m = 2 demo's 64-leaf trees cannot amortise.
-pub const MIN_GPU_LEAVES: usize = 1 << 10;
+/// one synchronisation; measured through the C ABI (profiles/r02_small_commits.md) a 135-column commit costs 329 us at 64 leaves
+/// (CPU port: 272 us) and 350 us at 128 leaves (CPU port: 486 us), so the device path takes over from 128 leaves up.
+pub const MIN_GPU_LEAVES: usize = 1 << 7;
 
 /// Owner of a `pcs_batch*` (device-resident LDE rows, digests, cap, coefficients).
 pub struct DeviceBatch(pub(crate) *mut sys::pcs_batch);

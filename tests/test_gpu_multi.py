@@ -429,3 +429,41 @@ def test_coset_intt_dev_matches_host_entry_point(pcs, w, lg_n):
     host = vals.copy()
     _ffi.check(_ffi.lib().pcs_coset_intt(_ffi.ptr(host), w, lg_n, shift))
     assert np.array_equal(host, coeffs)
+
+
+# ---------------------------------------------------------------------------------------------
+# the latency form of Poseidon (one permutation per half-warp, poseidon_coop.cuh): every entry point that switches to it below
+# 8192 permutations per launch must agree with the throughput form and with the oracle
+# ---------------------------------------------------------------------------------------------
+def test_cooperative_poseidon_matches_oracle_and_throughput_form(pcs):
+    from plonky2_demo_b200.hashing import PoseidonHash, poseidon
+
+    rng = np.random.default_rng(21)
+    g = np.array(field_grid(), dtype=np.uint64)
+    nc = np.array([P, P + 1, (1 << 64) - 1, (1 << 64) - 2, 0xFFFFFFFF, 0xFFFFFFFF00000000, 0], dtype=np.uint64)
+    for n in (1, 2, 3, 7, 8, 33, 4097, 8192):            # <= 8192: latency form; odd counts leave half a warp idle
+        x = np.concatenate([rng.integers(0, 1 << 64, size=(n, 12), dtype=np.uint64)[: max(n - 2, 0)],
+                            g[rng.integers(0, g.size, size=(1, 12))], nc[rng.integers(0, nc.size, size=(1, 12))]])[:n]
+        assert np.array_equal(poseidon(x), oracle.poseidon(x)), n
+    big = rng.integers(0, 1 << 64, size=(8193, 12), dtype=np.uint64)     # throughput form
+    assert np.array_equal(poseidon(big)[:100], poseidon(big[:100]))
+    # two_to_one and hash_or_noop on both sides of the switch
+    for n in (5, 8192, 8193):
+        l = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+        r = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+        assert np.array_equal(PoseidonHash.two_to_one_batch(l, r), oracle.two_to_one(l, r))
+    for ln in (1, 4, 5, 8, 9, 135):
+        rows = rng.integers(0, 1 << 64, size=(100, ln), dtype=np.uint64)
+        assert np.array_equal(PoseidonHash.hash_or_noop_batch(rows), oracle.hash_or_noop(rows))
+
+
+@pytest.mark.parametrize("log_n,leaf_len,cap_height", [(13, 7, 0), (13, 135, 4), (14, 9, 0), (14, 32, 4), (16, 5, 2), (12, 135, 12), (7, 135, 1)])
+def test_merkle_trees_across_the_latency_switch(pcs, log_n, leaf_len, cap_height):
+    """trees whose leaf level / node levels sit on either side of the 8192-permutation switch between the throughput kernels
+    and the latency kernels (incl. the fused top-of-tree launches): digests and cap == oracle"""
+    rng = np.random.default_rng(log_n * 100 + leaf_len)
+    leaves = rng.integers(0, 1 << 64, size=(1 << log_n, leaf_len), dtype=np.uint64)
+    t = pcs.MerkleTree.new(leaves, cap_height)
+    digests, cap = oracle.merkle_build(leaves, cap_height)
+    assert np.array_equal(t.cap.hashes, cap)
+    assert np.array_equal(t.digests, digests)
