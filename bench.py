@@ -384,8 +384,14 @@ def multi_in_process_bench(a, world, cap_expected):
     res["device_inputs"] = {"ms": float(np.median(ts[2:])), "ms_min": float(min(ts[2:])), "cap_equal": bool(np.array_equal(cap, cap_expected)),
                             "elems_per_s": w * (d << r) / (float(np.median(ts[2:])) * 1e-3),
                             "phase_ms_max_over_devices": {"FFT + blinding (peer loads)": ph[1], "leaf hashing": ph[3], "node levels": ph[4]}}
-    res["note"] = ("one process, one worker thread per GPU inside libpcs.so; exchange = first NTT pass reads the other GPUs' coefficient "
-                   "blocks over NVLink (no collective); wall-clock of the synchronous C call incl. the cap D2H")
+    ts, ph = run(dp, _ffi.PCS_DEVICE_PTRS | _ffi.PCS_MULTI_CE_GATHER, 2 + a.steps)
+    res["device_inputs_ce_gather"] = {"ms": float(np.median(ts[2:])), "ms_min": float(min(ts[2:])), "cap_equal": bool(np.array_equal(cap, cap_expected)),
+                                       "phase_ms_max_over_devices": {"FFT + blinding (incl. waits for the gather)": ph[1], "leaf hashing": ph[3], "node levels": ph[4]}}
+    ts, ph = run(hp, _ffi.PCS_MULTI_CE_GATHER, 2 + a.steps)
+    res["host_inputs_ce_gather"] = {"ms": float(np.median(ts[2:])), "ms_min": float(min(ts[2:])), "cap_equal": bool(np.array_equal(cap, cap_expected))}
+    res["note"] = ("one process, one worker thread per GPU inside libpcs.so, no collective library; exchange = the first NTT pass reads the other "
+                   "GPUs' coefficient blocks over NVLink in place (default), or -- *_ce_gather -- copy-engine gathers of polynomial group "
+                   "c+1 under the LDE + hashing of group c; wall-clock of the synchronous C call incl. the cap D2H")
     del tens, full
     return res
 

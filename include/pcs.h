@@ -56,7 +56,8 @@ typedef enum {
 
 enum {
     PCS_DEVICE_PTRS = 1u << 0,   /* input polynomial pointers are device pointers (no H2D copy)         */
-    PCS_KEEP_COEFFS = 1u << 1    /* keep the coefficient vectors on the device (PolynomialBatch.polynomials) */
+    PCS_KEEP_COEFFS = 1u << 1,   /* keep the coefficient vectors on the device (PolynomialBatch.polynomials) */
+    PCS_MULTI_CE_GATHER = 1u << 2    /* pcs_multi_*: exchange by copy-engine gathers instead of peer loads inside the first NTT pass (slower; kept for A/B) */
 };
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
@@ -228,8 +229,9 @@ PCS_API int pcs_timing_totals(float ms[5], unsigned* n_commits, int reset);
 /* ---- one commitment over several GPUs of this box from ONE host process -----------------------------
  * The reference's caller is a single Rust thread (prove(), plonk/prover.rs:145,212,260); these entry points let it use a
  * whole 8 x B200 box without a process per GPU: the library keeps a context and a worker thread per device, device g
- * extends and hashes the coset blocks [g 2^r / G, (g+1) 2^r / G) (= a contiguous leaf range = whole cap subtrees), and the
- * coefficient exchange is fused into the first NTT pass, which reads the other devices' blocks over NVLink in place.
+ * extends and hashes the coset blocks [g 2^r / G, (g+1) 2^r / G) (= a contiguous leaf range = whole cap subtrees).  The
+ * coefficient exchange is fused into the first NTT pass, which reads the other devices' blocks over NVLink in place
+ * (PCS_MULTI_CE_GATHER: copy-engine gathers of polynomial group c+1 under the compute of group c instead -- measured slower).
  * Results are bit-identical to pcs_commit_from_* on one GPU.  n_devices: a power of two, <= 2^rate_bits.            */
 typedef struct pcs_multi_batch pcs_multi_batch;
 /* devices == NULL: the first n_devices visible devices (all of them, rounded down to a power of two, when n_devices <= 0). */

@@ -14,6 +14,7 @@ sz = C.c_size_t
 
 PCS_DEVICE_PTRS = 1
 PCS_KEEP_COEFFS = 2
+PCS_MULTI_CE_GATHER = 4
 
 # every symbol include/pcs.h declares: name -> (restype, argtypes)
 SIGNATURES = {

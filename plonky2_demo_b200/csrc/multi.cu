@@ -10,11 +10,16 @@
 // a contiguous leaf range = whole cap subtrees = a contiguous slice of the reference's `digests` (merkle_tree.rs:43-46).
 // It needs every polynomial's coefficients and nobody's LDE output.
 //
-// Exchange = peer memory, fused with compute: every device holds a block of the polynomials (its share of each H2D chunk);
+// Exchange = peer memory, fused with compute (default): every device holds a block of the polynomials (its share of each H2D chunk);
 // the first NTT pass of every device follows a per-polynomial pointer table and loads the other devices' coefficients
 // straight from their HBM over NVLink / NVSwitch (k_ntt_pass, PassArgs::in_ptrs) -- no staging copy, no collective, the
 // transfer is hidden behind the butterflies.  Cross-device ordering is one cudaStreamWaitEvent per (peer, chunk): inside
 // one process an event recorded on device p's copy stream can be waited on by device q's compute stream.
+// PCS_MULTI_CE_GATHER selects the other exchange that was built and measured: every device PULLS the other devices' parts of
+// polynomial group c+1 into a local copy with peer cudaMemcpyAsync (copy engines, no SMs) while it extends and hashes group c.
+// On 8 x B200 it loses clearly (device-resident inputs: 28.8 ms per commitment against 17.1 ms with the fused peer loads; host
+// inputs 22.0 against 20.3 ms, profiles/r02_scaling.md): eight devices pulling 118 x 8 MB each through the copy engines reach
+// ~70 GB/s per device, while the NTT pass streams the same bytes at NVLink speed behind its butterflies.
 // Host inputs are cut into chunks so that the LDE of chunk c runs while chunk c+1 crosses PCIe on every device at once.
 #include <atomic>
 #include <mutex>
@@ -46,7 +51,9 @@ struct Multi {
     std::vector<int> devices;
     std::vector<cudaStream_t> copy_stream;              // per device
     std::vector<std::vector<FreeBlock>> free_blocks;    // per device: cudaMalloc'ed coefficient blocks kept for reuse
-    std::vector<std::vector<cudaEvent_t>> chunk_ev;     // [device][chunk]
+    std::vector<std::vector<cudaEvent_t>> chunk_ev;     // [device][chunk]: "my part of chunk c is in my block"
+    std::vector<cudaStream_t> gather_stream;            // per device: copy-engine pulls of the other devices' parts
+    std::vector<std::vector<cudaEvent_t>> gather_ev;    // [device][chunk]: "all of chunk c is in my local copy"
 };
 Multi g_multi;
 std::recursive_mutex g_multi_mutex;   // one multi commit at a time (recursive: a failing commit frees its batch under the lock)
@@ -136,7 +143,9 @@ void multi_shutdown_locked() {
         cudaDeviceSynchronize();
         for (auto& b : g_multi.free_blocks[gi]) cudaFree(b.p);
         for (auto& e : g_multi.chunk_ev[gi]) cudaEventDestroy(e);
+        for (auto& e : g_multi.gather_ev[gi]) cudaEventDestroy(e);
         if (g_multi.copy_stream[gi]) cudaStreamDestroy(g_multi.copy_stream[gi]);
+        if (g_multi.gather_stream[gi]) cudaStreamDestroy(g_multi.gather_stream[gi]);
     }
     g_multi = Multi();
     cudaGetLastError();
@@ -199,13 +208,18 @@ int pcs_multi_init(const int* devices, int n_devices) {
     g_multi.copy_stream.assign(n, nullptr);
     g_multi.free_blocks.assign(n, {});
     g_multi.chunk_ev.assign(n, {});
+    g_multi.gather_stream.assign(n, nullptr);
+    g_multi.gather_ev.assign(n, {});
     for (int i = 0; i < n; i++) {
         PCS_CUDA(cudaSetDevice(devs[i]));
         PCS_CUDA(cudaStreamCreateWithFlags(&g_multi.copy_stream[i], cudaStreamNonBlocking));
+        PCS_CUDA(cudaStreamCreateWithFlags(&g_multi.gather_stream[i], cudaStreamNonBlocking));
         for (size_t c = 0; c < MULTI_MAX_CHUNKS; c++) {
             cudaEvent_t ev;
             PCS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             g_multi.chunk_ev[i].push_back(ev);
+            PCS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            g_multi.gather_ev[i].push_back(ev);
         }
     }
     g_multi.init = true;
@@ -275,8 +289,11 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
     // host inputs: pipeline the H2D copies under the compute.  rho = transfer / compute time per polynomial: one device moves a
     // polynomial in ~0.15 ms against ~0.9 ms of LDE + hashing (2^20, rate 3); with 8 devices copying at once the host side
     // saturates and the ratio approaches 0.75 (profiles/r02_scaling.md)
+    const bool gather = G > 1 && (flags & PCS_MULTI_CE_GATHER);
     double rho = 0;
     if (staged && !from_values && !dev_ptrs && w * d * 8 >= ((size_t)G << 24)) rho = G >= 4 ? 0.75 : (G == 2 ? 0.4 : 0.25);
+    // device-resident inputs, gathered by the copy engines: an NVLink pull is ~10x faster than the compute on what it brings
+    if (!staged && gather && w * d * 8 >= ((size_t)G << 24)) rho = 0.1;
     plan.make_chunks(rho);
     if (plan.chunks > MULTI_MAX_CHUNKS) return fail(PCS_ERR_ARG, "internal: too many chunks");
     const size_t n_local_cap = (size_t)1 << plan.local_cap_height;
@@ -297,7 +314,7 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
             PCS_CUDA(cudaSetDevice(g_multi.devices[g]));
             block[g] = block_take(g, block_bytes(plan.rows_of(g), d));
             if (!block[g]) return fail(PCS_ERR_ALLOC, "coefficient block allocation failed on device " + std::to_string(g_multi.devices[g]));
-            if (keep) {
+            if (keep && !(G > 1 && (flags & PCS_MULTI_CE_GATHER))) {   // peer-load form: the blocks ARE `polynomials`
                 mb->owned_blocks.push_back(block[g]);
                 mb->owned_block_dev.push_back(g);
             }
@@ -314,10 +331,27 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
     } else {
         for (size_t j = 0; j < w; j++) mb->poly_ptr[j] = polys[j];
     }
+    // copy-engine gather: a local [w][d] copy of all coefficients per device (what the LDE then reads at HBM speed)
+    std::vector<uint64_t*> gath(G, nullptr);
+    if (gather)
+        for (int g = 0; g < G; g++) {
+            PCS_CUDA(cudaSetDevice(g_multi.devices[g]));
+            gath[g] = block_take(g, w * d * 8);
+            if (!gath[g]) return fail(PCS_ERR_ALLOC, "gather buffer allocation failed on device " + std::to_string(g_multi.devices[g]));
+        }
+    std::vector<const uint64_t*> src_ptr = mb->poly_ptr;    // where every polynomial's coefficients are BEFORE the gather
+    if (gather && keep) {
+        // PolynomialBatch.polynomials = device 0's gathered copy (one contiguous matrix); the staging blocks go back to the pool
+        mb->owned_blocks.assign(1, gath[0]);
+        mb->owned_block_dev.assign(1, 0);
+        for (size_t j = 0; j < w; j++) mb->poly_ptr[j] = gath[0] + j * d;
+    }
     auto release_blocks = [&]() {
-        if (staged && !keep)
+        if (staged && !(keep && !gather))
             for (int g = 0; g < G; g++)
                 if (block[g]) g_multi.free_blocks[g].push_back({block[g], block_bytes(plan.rows_of(g), d)});
+        for (int g = 0; g < G; g++)
+            if (gath[g] && !(keep && g == 0)) g_multi.free_blocks[g].push_back({gath[g], w * d * 8});
     };
 
     // ---- one worker thread per device ----
@@ -335,19 +369,39 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
             rc = pcs_shard_begin(w, salt_w, lg_d, rate_bits, (unsigned)g << plan.lg_cosets, plan.lg_cosets, plan.local_cap_height, &sh);
             if (rc) return rc;
             mb->shard[g] = sh;
+            cudaStream_t gs = g_multi.gather_stream[g];
+            std::vector<const uint64_t*> local_ptr;
             auto extend_chunk = [&](size_t c) -> int {
                 size_t lo, hi;
                 plan.chunk_range(c, lo, hi);
                 if (hi == lo) return PCS_OK;
+                cudaStream_t waiter = gather ? gs : st;      // who has to see the other devices' parts of this chunk
                 if (staged)
                     for (int q = 0; q < G; q++) {
                         while (!recorded[q * MULTI_MAX_CHUNKS + c].load(std::memory_order_acquire)) {
                             if (abort_flag.load()) return fail(PCS_ERR_CUDA, "another device's worker failed");
                             std::this_thread::yield();
                         }
-                        PCS_CUDA(cudaStreamWaitEvent(st, g_multi.chunk_ev[q][c], 0));
+                        PCS_CUDA(cudaStreamWaitEvent(waiter, g_multi.chunk_ev[q][c], 0));
                     }
-                return pcs_shard_extend(sh, lo, hi - lo, mb->poly_ptr.data() + lo);
+                if (!gather) return pcs_shard_extend(sh, lo, hi - lo, src_ptr.data() + lo);
+                // pull every part of the chunk into the local copy (peer copies over NVLink on the copy engines)
+                if (staged) {
+                    for (int q = 0; q < G; q++) {
+                        size_t a, b;
+                        plan.part(c, q, a, b);
+                        if (b > a)
+                            PCS_CUDA(cudaMemcpyAsync(gath[g] + a * d, src_ptr[a], (b - a) * d * 8, cudaMemcpyDefault, gs));
+                    }
+                } else {
+                    for (size_t j = lo; j < hi; j++)
+                        PCS_CUDA(cudaMemcpyAsync(gath[g] + j * d, src_ptr[j], d * 8, cudaMemcpyDefault, gs));
+                }
+                PCS_CUDA(cudaEventRecord(g_multi.gather_ev[g][c], gs));
+                PCS_CUDA(cudaStreamWaitEvent(st, g_multi.gather_ev[g][c], 0));
+                local_ptr.resize(hi - lo);
+                for (size_t j = lo; j < hi; j++) local_ptr[j - lo] = gath[g] + j * d;
+                return pcs_shard_extend(sh, lo, hi - lo, local_ptr.data());
             };
             if (staged) {
                 size_t row = 0;
@@ -396,8 +450,10 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
                     }
                 }
             } else {
-                rc = extend_chunk(0);
-                if (rc) return rc;
+                for (size_t c = 0; c < plan.chunks; c++) {
+                    rc = extend_chunk(c);
+                    if (rc) return rc;
+                }
             }
             // ---- blinding: the caller's salt columns are in natural LDE order (oracle.rs:119-123); this shard takes the
             //      leaf-order slice of its own leaf range ----
@@ -426,6 +482,7 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
         }
         cudaStreamSynchronize((cudaStream_t)pcs_stream());
         cudaStreamSynchronize(g_multi.copy_stream[g]);
+        cudaStreamSynchronize(g_multi.gather_stream[g]);
     };
     const int prev = pcs_device();
     if (G == 1) {

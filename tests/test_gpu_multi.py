@@ -226,6 +226,10 @@ def test_multi_commit_matches_oracle(pcs, n_dev):
             coeffs = seeded_polys(w, 1 << lg_d, base_seed=0xC0FFEE + w)
             coeffs[0, :2] = [P + 3, (1 << 64) - 1]       # non-canonical input coefficients
             ref = oracle.commit_from_coeffs(coeffs, r, cap_h)
+            # the other exchange: copy-engine gathers instead of peer loads fused into the first NTT pass
+            h, cap = _multi_commit(L, _ffi, coeffs, lg_d, r, cap_h, flags=_ffi.PCS_MULTI_CE_GATHER)
+            assert np.array_equal(cap, ref["cap"])
+            L.pcs_multi_batch_free(h)
             h, cap = _multi_commit(L, _ffi, coeffs, lg_d, r, cap_h)
             _check_multi_against_oracle(L, _ffi, h, cap, ref, w, lg_d + r, cap_h, rng)
             nl, ll, ns, ch = C.c_size_t(), C.c_size_t(), C.c_int(), C.c_uint()
@@ -280,7 +284,7 @@ def test_multi_commit_device_pointers_and_single_gpu_equivalence(pcs):
     L.pcs_shutdown()
     _ffi.check(L.pcs_multi_init(None, n_dev))
     try:
-        w, lg_d, r, cap_h = 33, 13, 3, 4
+        w, lg_d, r, cap_h = 33, 17, 3, 4          # 35 MB: several polynomial groups in the gather pipeline
         d = 1 << lg_d
         coeffs = seeded_polys(w, d, base_seed=0xDE71CE)
         tens = [torch.from_numpy(coeffs[j].view(np.int64)).to(f"cuda:{j % n_dev}") for j in range(w)]
@@ -289,7 +293,12 @@ def test_multi_commit_device_pointers_and_single_gpu_equivalence(pcs):
         ptrs = (_ffi.u64p * w)(*[C.cast(C.c_void_p(t.data_ptr()), _ffi.u64p) for t in tens])
         cap = np.empty((1 << cap_h, 4), dtype=np.uint64)
         h = C.c_void_p()
+        _ffi.check(L.pcs_multi_commit_from_coeffs(ptrs, w, lg_d, r, cap_h, None, 0, _ffi.PCS_DEVICE_PTRS | _ffi.PCS_MULTI_CE_GATHER,
+                                                  _ffi.ptr(cap), C.byref(h)))
+        cap_peer = cap.copy()
+        L.pcs_multi_batch_free(h)
         _ffi.check(L.pcs_multi_commit_from_coeffs(ptrs, w, lg_d, r, cap_h, None, 0, _ffi.PCS_DEVICE_PTRS, _ffi.ptr(cap), C.byref(h)))
+        assert np.array_equal(cap, cap_peer)
         ms = (C.c_float * 5)()
         _ffi.check(L.pcs_multi_batch_timings(h, ms))
         assert ms[3] > 0
