@@ -154,8 +154,9 @@ def cpu_baseline(a):
 
 def run_reference(a):
     """--impl reference: the CPU port of the reference path on ALL host cores (whatever OMP_NUM_THREADS torchrun exported).
-    K bounded-sample steps (135 x 2^cpu_sample_lg_d), then -- when it fits the time and memory budget -- the FULL
-    configuration itself (one run; every step when K <= 3), which then is the reported value.  Rank 0 only."""
+    The K timed steps are K - 1 bounded samples (135 x 2^cpu_sample_lg_d) and ONE commit of the full configuration (all K full-size
+    when K <= 3); the full-size step is dropped -- and says so -- when it would not fit the time / memory budget.
+    value = elements committed in the timed region / its duration.  Rank 0 only; the other ranks exit at once."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -165,42 +166,48 @@ def run_reference(a):
     lg = min(a.cpu_sample_lg_d, a.lg_d)
     for _ in range(min(a.warmup, 2)):
         cpu_commit_once(a.width, lg, a.rate_bits, a.cap_height)
-    times = []
-    for _ in range(a.steps):
-        dt, _ = cpu_commit_once(a.width, lg, a.rate_bits, a.cap_height)
-        times.append(dt)
-    total = sum(times)
     elems_s = a.width * (1 << (lg + a.rate_bits))
-    sample_value = elems_s * a.steps / total
-    sample = (f"{a.steps} steps, each one from_coeffs commit of {a.width} x 2^{lg} (rate_bits {a.rate_bits}, cap_height {a.cap_height}) "
-              f"= a bounded sample of the 2^{a.lg_d} workload, elems/s size-normalised; {cores} OpenMP threads")
-    value, ms_per_step, same = sample_value, 1e3 * total / a.steps, lg == a.lg_d
-    full = None
     elems_f = a.width * (1 << (a.lg_d + a.rate_bits))
+    # probe: one sample step decides whether the full configuration fits
+    probe, _ = cpu_commit_once(a.width, lg, a.rate_bits, a.cap_height)
+    n_full, skipped = 0, None
     if lg < a.lg_d and a.reference_full_size != "off":
-        predicted = (total / a.steps) * (1 << (a.lg_d - lg)) * 1.4        # cache effects make the big case slower per element
-        n_full = a.steps if a.steps <= 3 else 1
-        need = int(elems_f * 8 * 2.6)                                      # LDE + transposed leaves + coefficients + digests
+        want = a.steps if a.steps <= 3 else 1
+        predicted = probe * (1 << (a.lg_d - lg)) * 1.4            # cache effects make the big case slower per element
+        need = int(elems_f * 8 * 2.6)                              # LDE + transposed leaves + coefficients + digests
         avail = _mem_available_bytes()
-        if a.reference_full_size == "on" or (predicted * n_full <= a.reference_budget_s and avail >= need):
-            ft = []
-            for _ in range(n_full):
-                dt, _ = cpu_commit_once(a.width, a.lg_d, a.rate_bits, a.cap_height)
-                ft.append(dt)
-            full = {"runs": n_full, "s_per_commit": ft, "value": elems_f * n_full / sum(ft), "unit": UNIT}
-            value, ms_per_step, same = full["value"], 1e3 * sum(ft) / n_full, True
-            sample = (f"the full configuration: {n_full} from_coeffs commit(s) of {a.width} x 2^{a.lg_d} ({sum(ft) / n_full:.1f} s each) on "
-                      f"{cores} OpenMP threads, after {a.steps} sample steps at 2^{lg} ({sample_value:.3e} elems/s)")
+        if a.reference_full_size == "on" or (predicted * want <= a.reference_budget_s and avail >= need):
+            n_full = want
         else:
-            full = {"skipped": f"predicted {predicted * n_full:.0f} s (budget {a.reference_budget_s} s), needs {need >> 30} GiB of host memory "
-                               f"({avail >> 30} GiB available)"}
+            skipped = (f"predicted {predicted * want:.0f} s (budget {a.reference_budget_s} s), needs {need >> 30} GiB of host memory "
+                       f"({avail >> 30} GiB available)")
+    elif lg == a.lg_d:
+        n_full = a.steps
+    sample_t, full_t = [], []
+    for k in range(a.steps):
+        if k >= a.steps - n_full and lg < a.lg_d:
+            dt, _ = cpu_commit_once(a.width, a.lg_d, a.rate_bits, a.cap_height)
+            full_t.append(dt)
+        else:
+            dt, _ = cpu_commit_once(a.width, lg, a.rate_bits, a.cap_height)
+            (full_t if lg == a.lg_d else sample_t).append(dt)
+    total = sum(sample_t) + sum(full_t)
+    elems = elems_s * len(sample_t) + elems_f * len(full_t)
+    value = elems / total
+    sample = (f"{a.steps} timed steps on {cores} OpenMP threads: {len(sample_t)} bounded samples (one from_coeffs commit of {a.width} x 2^{lg} each"
+              f"{', %.2f s' % (sum(sample_t) / len(sample_t)) if sample_t else ''}) and {len(full_t)} commit(s) of the full {a.width} x 2^{a.lg_d} "
+              f"configuration{' (%.1f s each)' % (sum(full_t) / len(full_t)) if full_t else ''}; elems/s = elements committed / time"
+              + (f"; full-size step skipped: {skipped}" if skipped else ""))
     print(json.dumps({
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64 (Goldilocks field, integer)", "data": "synthetic",
         "config": bench_config(a),
-        "measured_on_full_config": same, "sample_value": sample_value, "full_size": full,
+        "measured_on_full_config": bool(full_t),
+        "sample_value": (elems_s * len(sample_t) / sum(sample_t)) if sample_t else None,
+        "full_size": ({"runs": len(full_t), "s_per_commit": full_t, "value": elems_f * len(full_t) / sum(full_t), "unit": UNIT} if full_t
+                      else {"skipped": skipped}),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
