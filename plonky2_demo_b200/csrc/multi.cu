@@ -309,6 +309,30 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
 
     // ---- coefficient blocks (staged inputs): device g holds its rows of every chunk, chunk after chunk ----
     std::vector<uint64_t*> block(G, nullptr);
+    std::vector<uint64_t*> gath(G, nullptr);
+    const int prev = pcs_device();
+    // on EVERY exit: blocks this call does not hand to the batch go back to the per-device pool, and the calling thread gets its
+    // current device / context back (the loops below walk the devices)
+    struct Cleanup {
+        std::vector<uint64_t*>& block;
+        std::vector<uint64_t*>& gath;
+        pcs_multi_batch* mb;
+        const Plan& plan;
+        size_t d, w;
+        int prev;
+        ~Cleanup() {
+            auto owned = [&](uint64_t* p) {
+                for (auto* o : mb->owned_blocks)
+                    if (o == p) return true;
+                return false;
+            };
+            for (size_t g = 0; g < block.size(); g++) {
+                if (block[g] && !owned(block[g])) g_multi.free_blocks[g].push_back({block[g], block_bytes(plan.rows_of((int)g), d)});
+                if (gath[g] && !owned(gath[g])) g_multi.free_blocks[g].push_back({gath[g], w * d * 8});
+            }
+            pcs_init(prev >= 0 ? prev : g_multi.devices[0], nullptr);
+        }
+    } cleanup{block, gath, mb, plan, d, w, prev};
     if (staged) {
         for (int g = 0; g < G; g++) {
             PCS_CUDA(cudaSetDevice(g_multi.devices[g]));
@@ -332,7 +356,6 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
         for (size_t j = 0; j < w; j++) mb->poly_ptr[j] = polys[j];
     }
     // copy-engine gather: a local [w][d] copy of all coefficients per device (what the LDE then reads at HBM speed)
-    std::vector<uint64_t*> gath(G, nullptr);
     if (gather)
         for (int g = 0; g < G; g++) {
             PCS_CUDA(cudaSetDevice(g_multi.devices[g]));
@@ -346,14 +369,6 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
         mb->owned_block_dev.assign(1, 0);
         for (size_t j = 0; j < w; j++) mb->poly_ptr[j] = gath[0] + j * d;
     }
-    auto release_blocks = [&]() {
-        if (staged && !(keep && !gather))
-            for (int g = 0; g < G; g++)
-                if (block[g]) g_multi.free_blocks[g].push_back({block[g], block_bytes(plan.rows_of(g), d)});
-        for (int g = 0; g < G; g++)
-            if (gath[g] && !(keep && g == 0)) g_multi.free_blocks[g].push_back({gath[g], w * d * 8});
-    };
-
     // ---- one worker thread per device ----
     std::vector<std::atomic<int>> recorded(G * MULTI_MAX_CHUNKS);   // chunk_ev[g][c] has been recorded
     for (auto& r : recorded) r.store(0);
@@ -484,7 +499,6 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
         cudaStreamSynchronize(g_multi.copy_stream[g]);
         cudaStreamSynchronize(g_multi.gather_stream[g]);
     };
-    const int prev = pcs_device();
     if (G == 1) {
         worker(0);
     } else {
@@ -492,13 +506,9 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
         for (int g = 0; g < G; g++) th.emplace_back(worker, g);
         for (auto& t : th) t.join();
     }
-    pcs_init(prev >= 0 ? prev : g_multi.devices[0], nullptr);
+    pcs_init(prev >= 0 ? prev : g_multi.devices[0], nullptr);   // pcs_two_to_one below runs on the caller's device
     for (int g = 0; g < G; g++)
-        if (rcs[g]) {
-            release_blocks();
-            return fail(rcs[g], "device " + std::to_string(g_multi.devices[g]) + ": " + errs[g]);
-        }
-    release_blocks();
+        if (rcs[g]) return fail(rcs[g], "device " + std::to_string(g_multi.devices[g]) + ": " + errs[g]);
     if (staged && !keep) mb->poly_ptr.clear();   // the blocks go back to the pool: PolynomialBatch.polynomials was not asked for
 
     // ---- cap: local caps in device order; above them log2(G) - cap_height levels of two_to_one (merkle_tree.rs:69-96) ----
