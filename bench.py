@@ -737,7 +737,18 @@ def run_ours(a):
     local_levels = (lg_d + plan.lg_cosets - plan.local_cap_height) if world > 1 else (lg_d + r - cap_h)
     # node levels: one launch per level while a level has more than 256 nodes per cap subtree, then ONE launch for the top of
     # every subtree; leaf hashing: one launch, or one per polynomial group of the streaming exchange (streaming sponge)
-    node_launches = max(local_levels - 9, 0) + (1 if local_levels >= 1 else 0)
+    def count_node_launches(n_leaves, lg_sub):
+        """mirror of node_levels_dev (csrc/api.cu): levels of > 8192 nodes (throughput form) or of <= 8192 nodes with more than 64
+        nodes per cap subtree (latency form) are one launch each, the rest of every subtree is ONE launch"""
+        k, level = 0, 1
+        while level <= lg_sub:
+            nodes, left = n_leaves >> level, lg_sub - level
+            if (left <= 6) if nodes <= 8192 else (left <= 8):
+                break
+            k += 1
+            level += 1
+        return k + (1 if level <= lg_sub else 0)
+    node_launches = count_node_launches(n // world, local_levels)
     launches_per_step = lg_passes * lde_groups + lde_groups + node_launches
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
