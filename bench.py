@@ -86,7 +86,7 @@ def parse():
                     help="N > 1: groups of the END-TO-END arm, where every group also crosses PCIe first.  auto = host:<rho> with "
                          "rho = transfer / compute time per polynomial (0.75 at N >= 4 where the host side saturates, 0.4 at N = 2): "
                          "geometrically growing groups, only the first 8-polynomial transfer is exposed")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer", "alltoall"],
                     help="N > 1: how coefficient blocks reach the other ranks (plonky2_demo_b200/sharded.py)")
     return ap.parse_args()
 
@@ -505,7 +505,7 @@ def run_ours(a):
 
     def chunk_spec(x):
         return int(x) if str(x).isdigit() else x
-    chunks = chunk_spec(a.chunks) if a.exchange != "peer" else 1
+    chunks = chunk_spec(a.chunks) if a.exchange not in ("peer", "alltoall") else 1
     plan = ShardPlan(w, lg_d, r, cap_h, world, chunks if world > 1 else 1)
     my_polys = plan.local_polys(rank) if world > 1 else list(range(w))
     w_loc = len(my_polys)
@@ -517,7 +517,7 @@ def run_ours(a):
     dev_coeffs = host.to(dev, non_blocking=False)
     # end-to-end arm: its own chunking (and therefore its own block distribution of the same W polynomials)
     e2e_spec = a.e2e_chunks if a.e2e_chunks != "auto" else f"host:{0.75 if world >= 4 else 0.4}"
-    e2e_chunks = chunk_spec(e2e_spec) if (a.exchange != "peer" and world > 1) else plan.sizes
+    e2e_chunks = chunk_spec(e2e_spec) if (a.exchange not in ("peer", "alltoall") and world > 1) else plan.sizes
     plan_e2e = ShardPlan(w, lg_d, r, cap_h, world, e2e_chunks if world > 1 else 1)
     if world > 1 and plan_e2e.sizes != plan.sizes and not a.no_e2e:
         polys_e2e = plan_e2e.local_polys(rank)

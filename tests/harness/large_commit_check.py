@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--rate-bits", type=int, default=3)
     ap.add_argument("--cap-height", type=int, default=4)
     ap.add_argument("--samples", type=int, default=3)
-    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "peer", "alltoall"])
     ap.add_argument("--chunks", type=int, default=2)
     ap.add_argument("--from-values", action="store_true",
                     help="start from point values: each rank IFFTs its own polynomials on its GPU (pcs_ntt_dev), then the sharded from_coeffs")
