@@ -813,7 +813,6 @@ static int commit_common(const uint64_t* const* polys, bool from_values, size_t 
             for (size_t j = 0; j < w; j++)
                 if (!polys[j]) return fail(PCS_ERR_ARG, "NULL polynomial pointer");
             pageable = w * d * 8 >= (8u << 20) && is_pageable_host(polys[0]);   // below 8 MB the threads cost more than they save
-            // pageable inputs: a chunk fills one ring slot, so that the staging threads are started once per 16 MB
             // Chunk sizes: the first transfer is the only one nothing hides, so it is small (8 polynomials = one absorb of the
             // sponge, or one 16 MB ring slot's worth for short polynomials); a chunk's compute (LDE + its share of the leaf
             // hashing, ~0.9 ms per polynomial at 2^20) outlasts a transfer 5x its size, so the groups grow 5x and few sponge
