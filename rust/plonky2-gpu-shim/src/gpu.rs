@@ -285,3 +285,90 @@ pub(crate) fn merkle_tree_new<F: RichField, H: Hasher<F>>(leaves: Vec<Vec<F>>, c
         device: None,
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// The batch's consumers in prove(): openings and the opening proof's composition polynomial
+// (SURVEY 8f N3 / N2).  D = 2 only: F::Extension = QuadraticExtension<GoldilocksField> = [u64; 2].
+// ------------------------------------------------------------------------------------------------
+use crate::field::extension::{Extendable, FieldExtension};
+use crate::fri::oracle::PolynomialBatch;
+use crate::fri::structure::FriInstanceInfo;
+use crate::plonk::config::GenericConfig;
+
+fn ext_to_words<F: RichField + Extendable<D>, const D: usize>(x: F::Extension) -> [u64; 2] {
+    let a = x.to_basefield_array();
+    [a[0].to_canonical_u64(), a[1].to_canonical_u64()]
+}
+
+fn ext_from_words<F: RichField + Extendable<D>, const D: usize>(w: &[u64]) -> F::Extension {
+    let mut a = [F::ZERO; D];
+    a[0] = F::from_canonical_u64(w[0]);
+    a[1] = F::from_canonical_u64(w[1]);
+    F::Extension::from_basefield_array(a)
+}
+
+/// Does this batch carry a device copy (with coefficients) that the opening kernels can read?
+pub(crate) fn has_device<F: RichField + Extendable<D>, C: GenericConfig<D, F = F>, const D: usize>(
+    c: &PolynomialBatch<F, C, D>,
+) -> bool {
+    D == 2 && c.merkle_tree.device.is_some()
+}
+
+/// `OpeningSet::new`'s `eval_commitment(z, c)`: `c.polynomials[j].to_extension().eval(z)` for every j
+/// (plonk/proof.rs:316-322) in one pass over the coefficients in HBM (pcs_batch_eval_ext, 3.8 TB/s).
+pub(crate) fn eval_commitment<F: RichField + Extendable<D>, C: GenericConfig<D, F = F>, const D: usize>(
+    z: F::Extension,
+    c: &PolynomialBatch<F, C, D>,
+) -> Vec<F::Extension> {
+    let dev = c.merkle_tree.device.as_ref().expect("has_device() was checked");
+    let point = ext_to_words::<F, D>(z);
+    let mut out = vec![0u64; 2 * c.polynomials.len()];
+    check(unsafe { sys::pcs_batch_eval_ext(dev.0, point.as_ptr(), out.as_mut_ptr()) });
+    out.chunks_exact(2).map(|w| ext_from_words::<F, D>(w)).collect()
+}
+
+/// The final polynomial of `PolynomialBatch::prove_openings` (fri/oracle.rs:171-200): per batch the alpha-reduction of its
+/// polynomials (`ReducingFactor::reduce_polys_base`), the quotient by (X - z_i) padded back to a power of two, and
+/// `shift_poly` -- computed on the device over the oracles' coefficients, d extension coefficients come back.
+pub(crate) fn final_poly<F: RichField + Extendable<D>, C: GenericConfig<D, F = F>, const D: usize>(
+    instance: &FriInstanceInfo<F, D>,
+    oracles: &[&PolynomialBatch<F, C, D>],
+    alpha: F::Extension,
+) -> PolynomialCoeffs<F::Extension> {
+    let handles: Vec<*const sys::pcs_batch> = oracles
+        .iter()
+        .map(|o| o.merkle_tree.device.as_ref().expect("has_device() was checked").0 as *const sys::pcs_batch)
+        .collect();
+    let mut points = Vec::with_capacity(2 * instance.batches.len());
+    let mut batch_len = Vec::with_capacity(instance.batches.len());
+    let (mut oracle_index, mut poly_index) = (Vec::new(), Vec::new());
+    for b in &instance.batches {
+        points.extend_from_slice(&ext_to_words::<F, D>(b.point));
+        batch_len.push(b.polynomials.len());
+        for p in &b.polynomials {
+            oracle_index.push(p.oracle_index as u32);
+            poly_index.push(p.polynomial_index as u32);
+        }
+    }
+    let alpha_w = ext_to_words::<F, D>(alpha);
+    let mut poly: *mut sys::pcs_ext_poly = core::ptr::null_mut();
+    check(unsafe {
+        sys::pcs_fri_final_poly(
+            handles.as_ptr(),
+            handles.len(),
+            instance.batches.len(),
+            points.as_ptr(),
+            batch_len.as_ptr(),
+            oracle_index.as_ptr(),
+            poly_index.as_ptr(),
+            alpha_w.as_ptr(),
+            &mut poly,
+        )
+    });
+    let mut len = 0usize;
+    check(unsafe { sys::pcs_ext_poly_len(poly, &mut len) });
+    let mut words = vec![0u64; 2 * len];
+    check(unsafe { sys::pcs_ext_poly_read(poly, words.as_mut_ptr()) });
+    unsafe { sys::pcs_ext_poly_free(poly) };
+    PolynomialCoeffs::new(words.chunks_exact(2).map(|w| ext_from_words::<F, D>(w)).collect())
+}

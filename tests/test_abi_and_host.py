@@ -238,7 +238,7 @@ def test_rust_shim_patches_apply_to_the_reference(tmp_path):
     if not os.path.isdir(os.path.join(ref, "plonky2", "src", "fri")):
         pytest.skip("no reference tree on this machine")
     patches = sorted(p for p in os.listdir(os.path.join(shim, "patches")) if p.endswith(".patch"))
-    assert len(patches) == 5
+    assert len(patches) == 6
     for p in patches:
         with open(os.path.join(shim, "patches", p)) as f:
             target = f.readline().split()[1][2:]          # "--- a/<path>"
