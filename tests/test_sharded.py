@@ -261,6 +261,10 @@ def _gloo_worker(rank, world, port, w, lg_d, r, cap, from_values, q, chunks=1, e
     (9, 5, 3, 4, False, 1, "auto", True), (9, 5, 2, 1, False, 2, "auto", True),   # salts through the coset partition, one-shot and streaming
 ])
 def test_gloo_world2_sharded_commit(w, lg_d, r, cap, from_values, chunks, exchange, blind):
+    _run_gloo_world(2, w, lg_d, r, cap, from_values, chunks, exchange, blind)
+
+
+def _run_gloo_world(world, w, lg_d, r, cap, from_values, chunks, exchange, blind):
     import socket
 
     import torch.multiprocessing as mp
@@ -271,13 +275,22 @@ def test_gloo_world2_sharded_commit(w, lg_d, r, cap, from_values, chunks, exchan
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_gloo_worker, args=(k, 2, port, w, lg_d, r, cap, from_values, q, chunks, exchange, blind)) for k in range(2)]
+    procs = [ctx.Process(target=_gloo_worker, args=(k, world, port, w, lg_d, r, cap, from_values, q, chunks, exchange, blind)) for k in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=120) for _ in procs)
+    res = sorted(q.get(timeout=180) for _ in procs)
     for p in procs:
         p.join(timeout=60)
-    assert res == [(0, True), (1, True)]
+    assert res == [(k, True) for k in range(world)]
+
+
+@pytest.mark.parametrize("w,lg_d,r,cap,exchange,blind", [
+    (6, 4, 1, 2, "auto", False),        # 4 ranks, 2 coset blocks: auto picks the all-to-all, half a coset per rank, cap subtrees split evenly
+    (3, 3, 2, 0, "alltoall", True),     # fewer polynomials than ranks (an empty block on the last rank), one root per rank + top levels, salts
+    (9, 4, 3, 4, "allgather", False),   # the coset partition on 4 ranks for comparison
+])
+def test_gloo_world4_partitions(w, lg_d, r, cap, exchange, blind):
+    _run_gloo_world(4, w, lg_d, r, cap, False, 1, exchange, blind)
 
 
 # ---------------------------------------------------------------------------------------------
