@@ -95,6 +95,12 @@ BatchScope::BatchScope(const pcs_batch* b) : prev(g_cur) {
 }
 BatchScope::~BatchScope() { ctx_enter((Ctx*)prev); }
 
+void* cur_ctx() { return g_cur; }
+CtxScope::CtxScope(void* ctx) : prev(g_cur) {
+    if (ctx) ctx_enter((Ctx*)ctx);
+}
+CtxScope::~CtxScope() { ctx_enter((Ctx*)prev); }
+
 pcs_batch* batch_new() {
     pcs_batch* b = new pcs_batch();
     b->ctx = g_cur;

@@ -59,6 +59,13 @@ struct BatchScope {
     explicit BatchScope(const pcs_batch* b);
     ~BatchScope();
 };
+// The same for any object that remembers the context it was made on (pcs_ext_poly): cur_ctx() at creation, CtxScope at use.
+void* cur_ctx();
+struct CtxScope {
+    void* prev;
+    explicit CtxScope(void* ctx);
+    ~CtxScope();
+};
 
 // stream-ordered temporary buffer
 struct DevBuf {

@@ -24,6 +24,7 @@ using namespace pcs;
 struct pcs_ext_poly {
     uint64_t* c = nullptr;   // [2][cap]: component e of coefficient i at c[e * cap + i]
     size_t len = 0, cap = 0;
+    void* ctx = nullptr;     // the engine context (device + stream) the coefficients live on
 };
 
 namespace {
@@ -565,6 +566,7 @@ static int ext_poly_alloc(size_t len, pcs_ext_poly** out, cudaStream_t st) {
     pcs_ext_poly* p = new pcs_ext_poly();
     p->len = len;
     p->cap = len ? len : 1;
+    p->ctx = cur_ctx();
     cudaError_t e = cudaMallocAsync((void**)&p->c, 2 * p->cap * 8, st);
     if (e != cudaSuccess) {
         delete p;
@@ -612,6 +614,7 @@ int pcs_ext_poly_read(const pcs_ext_poly* p, uint64_t* coeffs) {
     if (!p) return fail(PCS_ERR_ARG, "NULL pointer");
     if (p->len == 0) return PCS_OK;
     if (!coeffs) return fail(PCS_ERR_ARG, "NULL pointer");
+    CtxScope scope(p->ctx);
     cudaStream_t st = (cudaStream_t)pcs_stream();
     DevBuf tmp;
     PCS_CUDA(tmp.alloc(p->len * 16, st));
@@ -624,6 +627,7 @@ int pcs_ext_poly_read(const pcs_ext_poly* p, uint64_t* coeffs) {
 
 void pcs_ext_poly_free(pcs_ext_poly* p) {
     if (!p) return;
+    CtxScope scope(p->ctx);
     if (p->c) cudaFreeAsync(p->c, (cudaStream_t)pcs_stream());
     delete p;
 }
@@ -743,6 +747,7 @@ static int ext_lde(const pcs_ext_poly* p, unsigned rate_bits, uint64_t shift, ui
 int pcs_ext_coset_lde(const pcs_ext_poly* p, unsigned rate_bits, uint64_t shift, uint64_t* values) {
     if (int rc = need_init()) return rc;
     if (!p || !values) return fail(PCS_ERR_ARG, "NULL pointer");
+    CtxScope scope(p->ctx);
     cudaStream_t st = (cudaStream_t)pcs_stream();
     if (p->len == 0) return fail(PCS_ERR_ARG, "empty polynomial");
     const size_t n = p->len << rate_bits;
@@ -765,6 +770,7 @@ int pcs_fri_commit_layer(const pcs_ext_poly* p, unsigned rate_bits, uint64_t shi
     if (!tree) return fail(PCS_ERR_ARG, "tree is NULL");
     *tree = nullptr;
     if (!p || p->len == 0) return fail(PCS_ERR_ARG, "NULL or empty polynomial");
+    CtxScope scope(p->ctx);           // the tree is built (and its batch bound) where the polynomial lives
     cudaStream_t st = (cudaStream_t)pcs_stream();
     int lg_d = ilog2_strict(p->len);
     if (lg_d < 0) return fail(PCS_ERR_NOT_POW2, "Not a power of two: " + std::to_string(p->len));
@@ -807,6 +813,7 @@ int pcs_fri_fold(pcs_ext_poly* p, unsigned arity_bits, const uint64_t beta[2]) {
     if (arity_bits == 0) return PCS_OK;
     if (arity_bits > 31 || (p->len & (((size_t)1 << arity_bits) - 1)) || p->len == 0)
         return fail(PCS_ERR_ARG, "polynomial length is not a multiple of the arity (par_chunks_exact would drop coefficients)");
+    CtxScope scope(p->ctx);
     cudaStream_t st = (cudaStream_t)pcs_stream();
     const size_t n_out = p->len >> arity_bits;
     DevBuf o;
