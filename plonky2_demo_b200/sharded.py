@@ -33,6 +33,7 @@ partition / collective logic can be exercised on CPU (gloo, world_size 2) in tes
 substitutes it.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -445,7 +446,7 @@ class ShardedPolynomialBatch:
                 salt_rows = salt_leaf_slice(sal, plan.lg_d + rate_bits, lo_leaf, hi_leaf - lo_leaf)
             else:
                 # F::rand_vec (types.rs:33-35, OsRng): every rank draws the values of its own leaves
-                rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(16), "little"))
+                rng = np.random.default_rng(int.from_bytes(os.urandom(16), "little"))
                 salt_rows = rng.integers(0, 0xFFFFFFFF00000001, size=(4, hi_leaf - lo_leaf), dtype=np.uint64)
         if exchange == "alltoall" and world > 1:
             if not partitioned or plan.chunks > 1:
