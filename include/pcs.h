@@ -232,7 +232,9 @@ PCS_API int pcs_timing_totals(float ms[5], unsigned* n_commits, int reset);
  * extends and hashes the coset blocks [g 2^r / G, (g+1) 2^r / G) (= a contiguous leaf range = whole cap subtrees).  The
  * coefficient exchange is fused into the first NTT pass, which reads the other devices' blocks over NVLink in place
  * (PCS_MULTI_CE_GATHER: copy-engine gathers of polynomial group c+1 under the compute of group c instead -- measured slower).
- * Results are bit-identical to pcs_commit_from_* on one GPU.  n_devices: a power of two, <= 2^rate_bits.            */
+ * With more devices than coset blocks (n_devices > 2^rate_bits) the other partition is used: every device extends its own
+ * polynomials over all cosets and every device pulls its leaf range of every polynomial out of the owner's LDE (peer copies)
+ * into a row shard.  Results are bit-identical to pcs_commit_from_* on one GPU.  n_devices: a power of two, <= the leaf count. */
 typedef struct pcs_multi_batch pcs_multi_batch;
 /* devices == NULL: the first n_devices visible devices (all of them, rounded down to a power of two, when n_devices <= 0). */
 PCS_API int pcs_multi_init(const int* devices, int n_devices);

@@ -21,6 +21,11 @@
 // inputs 22.0 against 20.3 ms, profiles/r02_scaling.md): eight devices pulling 118 x 8 MB each through the copy engines reach
 // ~70 GB/s per device, while the NTT pass streams the same bytes at NVLink speed behind its butterflies.
 // Host inputs are cut into chunks so that the LDE of chunk c runs while chunk c+1 crosses PCIe on every device at once.
+//
+// More devices than coset blocks (n_devices > 2^rate_bits): the coset partition does not apply, so the other partition of
+// SURVEY 8e is used -- every device extends ITS polynomials over all cosets (pcs_coset_lde_dev) and every device pulls, for
+// every polynomial, the slice of its own leaf range out of the owner's LDE (peer cudaMemcpyAsync) straight into a row shard
+// (pcs_shard_begin_rows), then hashes.  Same results, same accessors; leaf ranges are fractions of a coset block.
 #include <atomic>
 #include <mutex>
 #include <thread>
@@ -33,6 +38,7 @@ struct pcs_multi_batch {
     size_t w = 0, salt_w = 0;
     unsigned lg_d = 0, rate_bits = 0, cap_height = 0;
     unsigned lg_dev = 0, lg_cosets = 0, local_cap_height = 0, top_levels = 0;
+    unsigned lg_local = 0;                         // log2(leaves per device)
     std::vector<pcs_batch*> shard;                 // per device
     std::vector<const uint64_t*> poly_ptr;         // [w] device address of every polynomial's coefficients (kept blocks or the caller's)
     std::vector<uint64_t*> owned_blocks;           // coefficient blocks this batch owns (PCS_KEEP_COEFFS / from_values)
@@ -272,26 +278,28 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
     plan.w = w;
     plan.lg_dev = 0;
     while ((1 << plan.lg_dev) < G) plan.lg_dev++;
-    if (plan.lg_dev > rate_bits)
-        return fail(PCS_ERR_ARG, "cannot split 2^" + std::to_string(rate_bits) + " coset blocks over " + std::to_string(G) +
-                                     " devices (pcs_multi needs n_devices <= 2^rate_bits; plonky2_demo_b200/sharded.py's "
-                                     "all-to-all mode lifts this)");
-    plan.lg_cosets = rate_bits - plan.lg_dev;
+    if (plan.lg_dev > lg_d + rate_bits)
+        return fail(PCS_ERR_ARG, "cannot split " + std::to_string((size_t)1 << (lg_d + rate_bits)) + " leaves over " + std::to_string(G) + " devices");
+    // more devices than coset blocks: polynomial-partitioned LDE + peer pulls of LDE rows into row shards
+    const bool rows_mode = plan.lg_dev > rate_bits;
+    plan.lg_cosets = rows_mode ? 0 : rate_bits - plan.lg_dev;
+    const unsigned lg_local = lg_d + rate_bits - plan.lg_dev;
     plan.local_cap_height = cap_height > plan.lg_dev ? cap_height - plan.lg_dev : 0;
     plan.top_levels = plan.lg_dev > cap_height ? plan.lg_dev - cap_height : 0;
-    if (plan.local_cap_height > lg_d + plan.lg_cosets)
+    if (plan.local_cap_height > lg_local)
         return fail(PCS_ERR_CAP_HEIGHT, "cap_height too large for the per-device leaf range");
     const bool dev_ptrs = flags & PCS_DEVICE_PTRS;
     const bool keep = from_values || (flags & PCS_KEEP_COEFFS);
     const size_t d = (size_t)1 << lg_d, n = d << rate_bits, n_loc = n >> plan.lg_dev;
     // device-resident inputs are read in place; host inputs arrive in chunks (H2D of chunk c+1 under the LDE of chunk c)
-    const bool staged = !dev_ptrs || from_values;   // from_values transforms in place: always on engine-owned blocks
+    const bool staged = !dev_ptrs || from_values || rows_mode;   // from_values transforms in place: always on engine-owned blocks;
+                                                                 // rows mode: every device extends the block it holds
     // host inputs: pipeline the H2D copies under the compute.  rho = transfer / compute time per polynomial: one device moves a
     // polynomial in ~0.15 ms against ~0.9 ms of LDE + hashing (2^20, rate 3); with 8 devices copying at once the host side
     // saturates and the ratio approaches 0.75 (profiles/r02_scaling.md)
-    const bool gather = G > 1 && (flags & PCS_MULTI_CE_GATHER);
+    const bool gather = G > 1 && (flags & PCS_MULTI_CE_GATHER) && !rows_mode;
     double rho = 0;
-    if (staged && !from_values && !dev_ptrs && w * d * 8 >= ((size_t)G << 24)) rho = G >= 4 ? 0.75 : (G == 2 ? 0.4 : 0.25);
+    if (staged && !from_values && !dev_ptrs && !rows_mode && w * d * 8 >= ((size_t)G << 24)) rho = G >= 4 ? 0.75 : (G == 2 ? 0.4 : 0.25);
     // device-resident inputs, gathered by the copy engines: an NVLink pull is ~10x faster than the compute on what it brings
     if (!staged && gather && w * d * 8 >= ((size_t)G << 24)) rho = 0.1;
     plan.make_chunks(rho);
@@ -302,6 +310,7 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
     mb->n_dev = G; mb->w = w; mb->salt_w = salt_w; mb->lg_d = lg_d; mb->rate_bits = rate_bits; mb->cap_height = cap_height;
     mb->lg_dev = plan.lg_dev; mb->lg_cosets = plan.lg_cosets; mb->local_cap_height = plan.local_cap_height;
     mb->top_levels = plan.top_levels;
+    mb->lg_local = lg_local;
     mb->shard.assign(G, nullptr);
     mb->poly_ptr.assign(w, nullptr);
     mb->local_caps.assign((size_t)G * n_local_cap * 4, 0);
@@ -320,6 +329,8 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
         const Plan& plan;
         size_t d, w;
         int prev;
+        size_t n = 0;          // rows mode: gath[g] holds rows_of(g) LDE rows of n elements
+        bool rows_mode = false;
         ~Cleanup() {
             auto owned = [&](uint64_t* p) {
                 for (auto* o : mb->owned_blocks)
@@ -328,11 +339,14 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
             };
             for (size_t g = 0; g < block.size(); g++) {
                 if (block[g] && !owned(block[g])) g_multi.free_blocks[g].push_back({block[g], block_bytes(plan.rows_of((int)g), d)});
-                if (gath[g] && !owned(gath[g])) g_multi.free_blocks[g].push_back({gath[g], w * d * 8});
+                if (gath[g] && !owned(gath[g]))
+                    g_multi.free_blocks[g].push_back({gath[g], rows_mode ? block_bytes(plan.rows_of((int)g), n) : w * d * 8});
             }
             pcs_init(prev >= 0 ? prev : g_multi.devices[0], nullptr);
         }
     } cleanup{block, gath, mb, plan, d, w, prev};
+    cleanup.n = n;
+    cleanup.rows_mode = rows_mode;
     if (staged) {
         for (int g = 0; g < G; g++) {
             PCS_CUDA(cudaSetDevice(g_multi.devices[g]));
@@ -355,6 +369,13 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
     } else {
         for (size_t j = 0; j < w; j++) mb->poly_ptr[j] = polys[j];
     }
+    // rows mode: the LDE of a device's own polynomials over all cosets, [rows_of(g)][N]; pulled from by every device
+    if (rows_mode)
+        for (int g = 0; g < G; g++) {
+            PCS_CUDA(cudaSetDevice(g_multi.devices[g]));
+            gath[g] = block_take(g, block_bytes(plan.rows_of(g), n));
+            if (!gath[g]) return fail(PCS_ERR_ALLOC, "LDE buffer allocation failed on device " + std::to_string(g_multi.devices[g]));
+        }
     // copy-engine gather: a local [w][d] copy of all coefficients per device (what the LDE then reads at HBM speed)
     if (gather)
         for (int g = 0; g < G; g++) {
@@ -381,7 +402,8 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
             if (rc) return rc;
             cudaStream_t st = (cudaStream_t)pcs_stream(), cst = g_multi.copy_stream[g];
             pcs_batch* sh = nullptr;
-            rc = pcs_shard_begin(w, salt_w, lg_d, rate_bits, (unsigned)g << plan.lg_cosets, plan.lg_cosets, plan.local_cap_height, &sh);
+            rc = rows_mode ? pcs_shard_begin_rows(w + salt_w, salt_w, lg_local, plan.local_cap_height, &sh)
+                           : pcs_shard_begin(w, salt_w, lg_d, rate_bits, (unsigned)g << plan.lg_cosets, plan.lg_cosets, plan.local_cap_height, &sh);
             if (rc) return rc;
             mb->shard[g] = sh;
             cudaStream_t gs = g_multi.gather_stream[g];
@@ -459,10 +481,43 @@ static int multi_commit(const uint64_t* const* polys, bool from_values, size_t w
                         recorded[g * MULTI_MAX_CHUNKS + c].store(1, std::memory_order_release);
                         row += b - a;
                     }
-                    if (c >= 1) {
+                    if (c >= 1 && !rows_mode) {
                         rc = extend_chunk(c - 1);
                         if (rc) return rc;
                     }
+                }
+                if (rows_mode) {
+                    // (1) the LDE of my block over all cosets, behind my staging copy / IFFT
+                    size_t a, b;
+                    plan.part(0, g, a, b);
+                    PCS_CUDA(cudaStreamWaitEvent(st, g_multi.chunk_ev[g][0], 0));
+                    if (b > a) {
+                        std::vector<const uint64_t*> mine(b - a);
+                        for (size_t j = a; j < b; j++) mine[j - a] = block[g] + (j - a) * d;
+                        rc = pcs_coset_lde_dev(mine.data(), b - a, lg_d, rate_bits, 7, gath[g]);
+                        if (rc) return rc;
+                    }
+                    PCS_CUDA(cudaEventRecord(g_multi.chunk_ev[g][1], st));
+                    recorded[g * MULTI_MAX_CHUNKS + 1].store(1, std::memory_order_release);
+                    // (2) pull my leaf range of every polynomial out of its owner's LDE, straight into the shard's rows
+                    uint64_t* rows = const_cast<uint64_t*>(pcs_batch_lde_dev(sh));
+                    cudaStream_t gs = g_multi.gather_stream[g];
+                    PCS_CUDA(cudaEventRecord(g_multi.gather_ev[g][1], st));          // the shard's buffer exists
+                    PCS_CUDA(cudaStreamWaitEvent(gs, g_multi.gather_ev[g][1], 0));
+                    for (int q = 0; q < G; q++) {
+                        while (!recorded[q * MULTI_MAX_CHUNKS + 1].load(std::memory_order_acquire)) {
+                            if (abort_flag.load()) return fail(PCS_ERR_CUDA, "another device's worker failed");
+                            std::this_thread::yield();
+                        }
+                        PCS_CUDA(cudaStreamWaitEvent(gs, g_multi.chunk_ev[q][1], 0));
+                        size_t qa, qb;
+                        plan.part(0, q, qa, qb);
+                        if (qb > qa)      // (qb - qa) rows of n_loc elements, source pitch n, destination pitch n_loc
+                            PCS_CUDA(cudaMemcpy2DAsync(rows + qa * n_loc, n_loc * 8, gath[q] + (size_t)g * n_loc, n * 8, n_loc * 8, qb - qa,
+                                                       cudaMemcpyDefault, gs));
+                    }
+                    PCS_CUDA(cudaEventRecord(g_multi.gather_ev[g][0], gs));
+                    PCS_CUDA(cudaStreamWaitEvent(st, g_multi.gather_ev[g][0], 0));
                 }
             } else {
                 for (size_t c = 0; c < plan.chunks; c++) {
@@ -598,7 +653,7 @@ int pcs_multi_batch_prove(const pcs_multi_batch* mb, size_t leaf_index, uint64_t
     if (!mb) return fail(PCS_ERR_ARG, "NULL pointer");
     const size_t n_leaves = ((size_t)1 << mb->lg_d) << mb->rate_bits, n_loc = n_leaves >> mb->lg_dev;
     if (leaf_index >= n_leaves) return fail(PCS_ERR_ARG, "leaf index out of bounds");
-    const unsigned n_local = mb->lg_d + mb->lg_cosets - mb->local_cap_height;
+    const unsigned n_local = mb->lg_local - mb->local_cap_height;
     if (n_local + mb->top_levels == 0) return PCS_OK;
     if (!siblings) return fail(PCS_ERR_ARG, "NULL pointer");
     const int g = (int)(leaf_index / n_loc);

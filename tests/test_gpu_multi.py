@@ -262,11 +262,29 @@ def test_multi_commit_matches_oracle(pcs, n_dev):
 
         assert np.array_equal(ev, fri_ref.eval_base_polys_ext(coeffs, (int(z[0]), int(z[1]))))
         L.pcs_multi_batch_free(h)
-        # errors: more devices than coset blocks, empty batch
+        # more devices than coset blocks (rate_bits < log2 n_dev): polynomial-partitioned LDE + peer pulls of LDE rows into row
+        # shards; leaf ranges are fractions of a coset block
+        if n_dev > 1:
+            lg_dev = n_dev.bit_length() - 1
+            for (w, lg_d, r, cap_h, blind) in [(7, 6, lg_dev - 1, 1, False), (3, 5, 0, 0, True), (20, 9, lg_dev - 1, 4, False),
+                                                (1, 3, 0, 2, False)]:
+                if cap_h > lg_d + r:
+                    continue
+                coeffs = seeded_polys(w, 1 << lg_d, base_seed=0xA2A + w)
+                salts = seeded_polys(4, 1 << (lg_d + r), base_seed=0x77 + w) if blind else None
+                ref = oracle.commit_from_coeffs(coeffs, r, cap_h, salts=salts)
+                h, cap = _multi_commit(L, _ffi, coeffs, lg_d, r, cap_h, salts=salts)
+                _check_multi_against_oracle(L, _ffi, h, cap, ref, w + (4 if blind else 0), lg_d + r, cap_h, rng)
+                L.pcs_multi_batch_free(h)
+                out = np.zeros_like(coeffs)
+                h, cap = _multi_commit(L, _ffi, oracle.fft(coeffs), lg_d, r, cap_h, salts=salts, from_values=True, coeffs_out=out)
+                assert np.array_equal(cap, ref["cap"]) and np.array_equal(out, coeffs)
+                L.pcs_multi_batch_free(h)
+        # errors: more devices than leaves, empty batch
         if n_dev > 2:
             hh = C.c_void_p()
-            c1 = seeded_polys(2, 16)
-            assert L.pcs_multi_commit_from_coeffs(_ffi.ptr_array([c1[0], c1[1]]), 2, 4, 1, 0, None, 0, 0, None, C.byref(hh)) != 0
+            c1 = seeded_polys(2, 1)
+            assert L.pcs_multi_commit_from_coeffs(_ffi.ptr_array([c1[0], c1[1]]), 2, 0, 1, 0, None, 0, 0, None, C.byref(hh)) != 0
         hh = C.c_void_p()
         assert L.pcs_multi_commit_from_coeffs(None, 0, 4, 3, 0, None, 0, 0, None, C.byref(hh)) != 0
     finally:
