@@ -627,3 +627,47 @@ def test_gloo_world2_opening_proof_over_sharded_commitments():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+# ---------------------------------------------------------------------------------------------
+# host helpers of the round-2 partitions (pure CPU)
+# ---------------------------------------------------------------------------------------------
+def test_chunk_specs_cover_every_polynomial_with_rate_aligned_boundaries():
+    """streaming groups: every spec covers [0, w) exactly once; all boundaries but the last are multiples of the sponge rate 8
+    (a group can only be hashed up to a multiple of 8 columns); "host:<rho>" groups obey b[k+2] <= b[1] + b[k+1] / rho"""
+    from plonky2_demo_b200.sharded import ShardPlan
+
+    for w in (1, 7, 8, 9, 16, 17, 84, 135, 1000):
+        for spec in (1, 2, 3, 4, 9, "host:0.75", "host:0.4", "host:0.16", [w]):
+            p = ShardPlan(w, 6, 3, 0, 4, spec)
+            assert p.bounds[0] == 0 and p.bounds[-1] == w and p.bounds == sorted(set(p.bounds)), (w, spec, p.bounds)
+            assert sum(p.sizes) == w and p.chunks == len(p.sizes)
+            if w > 16 and p.chunks > 1:
+                assert all(b % 8 == 0 for b in p.bounds[1:-1]), (w, spec, p.bounds)
+            if isinstance(spec, str) and p.chunks > 2:
+                rho = float(spec.split(":")[1])
+                b = p.bounds
+                assert all(b[k + 2] <= b[1] + b[k + 1] / rho + 8 for k in range(len(b) - 2)), (w, spec, b)
+            # every rank's polynomials, chunk by chunk, tile the chunk
+            for c in range(p.chunks):
+                lo, hi = p.chunk_range(c)
+                got = [j for k in range(4) for j in range(*p.poly_ranges(k)[c])]
+                assert got == list(range(lo, hi))
+    with pytest.raises(ValueError, match="must add up"):
+        ShardPlan(10, 4, 3, 0, 2, [4, 4])
+
+
+@pytest.mark.parametrize("lg_n,first,count", [(6, 0, 64), (6, 16, 16), (9, 384, 128), (3, 5, 3), (0, 0, 1)])
+def test_salt_leaf_slice_is_the_row_bit_reversal(lg_n, first, count):
+    """a rank's salt rows = the leaf-order slice of the natural-order salt columns: leaves[i] = column[reverse_bits(i)]
+    (reverse_index_bits_in_place on the rows, oracle.rs:84), checked against the oracle's transpose + bit-reversal"""
+    from plonky2_demo_b200.sharded import reverse_bits_array, salt_leaf_slice
+
+    n = 1 << lg_n
+    salts = seeded_polys(4, n, base_seed=0x5A17)
+    leaves = oracle.transpose_bitrev(salts)                     # [n][4] in leaf order
+    got = salt_leaf_slice(salts, lg_n, first, count)
+    assert got.shape == (4, count)
+    assert np.array_equal(got.T, leaves[first:first + count])
+    idx = np.arange(n, dtype=np.uint64)
+    assert np.array_equal(reverse_bits_array(reverse_bits_array(idx, lg_n), lg_n), idx)
