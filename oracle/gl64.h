@@ -65,7 +65,7 @@ static inline gl_t gl_reduce128(u128 x) {
     uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
     uint64_t hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
     uint64_t t0 = lo - hi_hi;
-    if (__builtin_expect(lo < hi_hi, 0)) t0 -= GL_EPS; /* "exceedingly rare" (goldilocks_field.rs:362) */
+    if (__builtin_expect(lo < hi_hi, 0)) { t0 -= GL_EPS; __asm__("" : "+r"(t0)); } /* "exceedingly rare" (goldilocks_field.rs:362) */
     uint64_t t1 = hi_lo * GL_EPS;
     return gl_add_no_canon(t0, t1);
 }

@@ -213,20 +213,72 @@ static inline void constant_layer(gl_t* s, int round) {
     for (int i = 0; i < PW; i++) s[i] = gl_add(s[i], ALL_ROUND_CONSTANTS[i + PW * round]);
 }
 
-/* poseidon.rs:178-198 mds_row_shf + :242-262 mds_layer.  The x86-64 override
- * (poseidon_goldilocks.rs:217-248) splits every lane in 32-bit halves so that all sums fit in
- * u64; we use the same split with the plain circulant sums (result identical). */
+/* One 32-bit half of the MDS product: y = circ-correlation(s) (exact in int64, inputs < 2^32, results
+ * < 2^43).  The 12-point circulant is evaluated through x^12 - 1 = prod over zeta in {1,-1,i,-i} of
+ * (x^3 - zeta) with x^4 = zeta: three 4-point integer DFTs, three 3x3 twisted products whose constants
+ * are [16,32,16], [-1,-8,2] and (2+i),(-4-i),(16-i), three inverse DFTs -- the decomposition the
+ * reference's x86-64 path uses (poseidon_goldilocks.rs:307-441 mds_multiply_freq), written here as the
+ * add/shift network tests/golden/make_golden.py:mds_network_check derives and checks against the plain
+ * circulant sums of poseidon.rs:178-198 mds_row_shf. */
+static inline void mds_half(const int64_t* s, int64_t* y) {
+    int64_t A[3], B[3], P[3], Q[3];
+    for (int j = 0; j < 3; j++) {
+        int64_t u = s[j] + s[j + 6], v = s[j + 3] + s[j + 9];
+        A[j] = u + v;
+        B[j] = u - v;
+        P[j] = s[j] - s[j + 6];
+        Q[j] = s[j + 3] - s[j + 9];
+    }
+    int64_t t = A[0] + A[1] + A[2];
+    int64_t Ya[3] = {(t + A[2]) << 4, (t + A[0]) << 4, (t + A[1]) << 4};
+    int64_t Yb[3] = {(B[2] << 3) - (B[1] << 1) - B[0], -(B[0] << 3) - B[1] - (B[2] << 1),
+                     (B[0] << 1) - (B[1] << 3) - B[2]};
+    int64_t re[3], im[3];
+    re[0] = (P[0] << 1) - Q[0] + P[1] - (Q[1] << 4) + P[2] + (Q[2] << 2);
+    im[0] = P[0] + (Q[0] << 1) + (P[1] << 4) + Q[1] - (P[2] << 2) + Q[2];
+    re[1] = -(P[0] << 2) + Q[0] + (P[1] << 1) - Q[1] + P[2] - (Q[2] << 4);
+    im[1] = -P[0] - (Q[0] << 2) + P[1] + (Q[1] << 1) + (P[2] << 4) + Q[2];
+    re[2] = (P[0] << 4) + Q[0] - (P[1] << 2) + Q[1] + (P[2] << 1) - Q[2];
+    im[2] = -P[0] + (Q[0] << 4) - P[1] - (Q[1] << 2) + P[2] + (Q[2] << 1);
+    for (int j = 0; j < 3; j++) {
+        int64_t e1 = Ya[j] + Yb[j], e2 = Ya[j] - Yb[j];
+        y[j] = e1 + re[j];
+        y[j + 3] = e2 + im[j];
+        y[j + 6] = e1 - re[j];
+        y[j + 9] = e2 - im[j];
+    }
+}
+
+/* poseidon.rs:242-262 mds_layer in the form of the x86-64 override (poseidon_goldilocks.rs:217-248):
+ * every lane is split in 32-bit halves so that both half-products fit in 64 bits, the halves are
+ * recombined to 96 bits and folded once; MDS_MATRIX_DIAG is 8 on lane 0 and 0 elsewhere. */
 static inline void mds_layer(gl_t* s) {
-    /* doubled halves so that the circulant index (i + r) needs no modulo */
+    int64_t lo[PW], hi[PW], yl[PW], yh[PW];
+    for (int i = 0; i < PW; i++) {
+        lo[i] = (int64_t)(uint32_t)s[i];
+        hi[i] = (int64_t)(s[i] >> 32);
+    }
+    mds_half(lo, yl);
+    mds_half(hi, yh);
+    yl[0] += lo[0] * (int64_t)MDS_MATRIX_DIAG[0];
+    yh[0] += hi[0] * (int64_t)MDS_MATRIX_DIAG[0];
+    for (int r = 0; r < PW; r++) {
+        u128 sum = (u128)(uint64_t)yl[r] + ((u128)(uint64_t)yh[r] << 32);
+        s[r] = gl_reduce96((uint64_t)sum, (uint32_t)(sum >> 64));
+    }
+}
+
+/* The plain circulant sums of poseidon.rs:178-198 mds_row_shf (what mds_layer computes on targets
+ * without the override); kept for ref_poseidon_permute(naive = 2), which tests/ compare with the
+ * network above on random states. */
+static inline void mds_layer_plain(gl_t* s) {
     uint64_t lo[2 * PW], hi[2 * PW], out[PW];
     for (int i = 0; i < PW; i++) {
         lo[i] = lo[i + PW] = (uint32_t)s[i];
         hi[i] = hi[i + PW] = s[i] >> 32;
     }
-#pragma GCC unroll 12
     for (int r = 0; r < PW; r++) {
         uint64_t al = 0, ah = 0;
-#pragma GCC unroll 12
         for (int i = 0; i < PW; i++) {
             al += lo[i + r] * MDS_MATRIX_CIRC[i];
             ah += hi[i + r] * MDS_MATRIX_CIRC[i];
@@ -263,17 +315,21 @@ static inline void partial_rounds_fast(gl_t* s, int* round) {
     const gl_t m00 = MDS_MATRIX_CIRC[0] + MDS_MATRIX_DIAG[0];
     for (int k = 0; k < N_PARTIAL; k++) {
         s[0] = gl_add(sbox(s[0]), FAST_PARTIAL_ROUND_CONSTANTS[k]);
-        /* d = [M00 | w_hat] . state, accumulated in (u128 lo, u32 hi) = "u160" */
-        u128 acc = (u128)s[0] * m00;
-        uint32_t acc_hi = 0;
+        /* d = [M00 | w_hat] . state as an exact 160-bit sum (poseidon.rs:30-44 add_u160_u128).  The
+         * low and high words of the 12 products are summed separately so that no carry has to be
+         * tested: a carry out of 128 bits happens on about every other term of random data, and a
+         * branch on it is mispredicted as often. */
+        u128 first = (u128)s[0] * m00;
+        u128 sum_lo = (uint64_t)first, sum_hi = (uint64_t)(first >> 64);
         for (int i = 1; i < PW; i++) {
             u128 term = (u128)s[i] * FAST_PARTIAL_ROUND_W_HATS[k * 11 + i - 1];
-            u128 nacc = acc + term;
-            acc_hi += nacc < acc;
-            acc = nacc;
+            sum_lo += (uint64_t)term;
+            sum_hi += (uint64_t)(term >> 64);
         }
+        sum_hi += (uint64_t)(sum_lo >> 64); /* < 2^68 */
         /* poseidon.rs:46-53 reduce_u160 */
-        uint64_t lo_hi = (uint64_t)(acc >> 64), lo_lo = (uint64_t)acc;
+        uint64_t lo_hi = (uint64_t)sum_hi, lo_lo = (uint64_t)sum_lo;
+        uint32_t acc_hi = (uint32_t)(sum_hi >> 64);
         gl_t red_hi = gl_reduce96(lo_hi, acc_hi);
         gl_t d = gl_reduce128(((u128)red_hi << 64) + lo_lo);
         for (int i = 1; i < PW; i++) s[i] = gl_add(s[i], gl_mul(s[0], FAST_PARTIAL_ROUND_VS[k * 11 + i - 1]));
@@ -308,11 +364,26 @@ static inline void poseidon_naive(gl_t* s) {
     full_rounds(s, &round);
 }
 
+/* poseidon_naive with the plain circulant MDS: no optimised form anywhere (the definition) */
+static void poseidon_plain(gl_t* s) {
+    for (int round = 0; round < 2 * HALF_FULL + N_PARTIAL; round++) {
+        constant_layer(s, round);
+        if (round < HALF_FULL || round >= HALF_FULL + N_PARTIAL)
+            for (int i = 0; i < PW; i++) s[i] = sbox(s[i]);
+        else
+            s[0] = sbox(s[0]);
+        mds_layer_plain(s);
+    }
+}
+
+/* naive: 0 = poseidon (fast partial rounds), 1 = poseidon_naive, 2 = the plain definition */
 API int ref_poseidon_permute(uint64_t* states /*[n][12]*/, size_t n, int naive) {
 #pragma omp parallel for
     for (size_t i = 0; i < n; i++) {
         gl_t* s = states + i * PW;
-        if (naive)
+        if (naive == 2)
+            poseidon_plain(s);
+        else if (naive)
             poseidon_naive(s);
         else
             poseidon(s);

@@ -56,14 +56,23 @@ def test_poseidon_kats(golden):
         x = np.array(kv["input"], dtype=np.uint64)
         assert oracle.poseidon(x)[0].tolist() == kv["output"]
         assert oracle.poseidon(x, naive=True)[0].tolist() == kv["output"]
+        assert oracle.poseidon(x, naive=2)[0].tolist() == kv["output"]  # plain circulant MDS, no fast form anywhere
 
 
 def test_poseidon_consistency_and_noncanonical():
     # poseidon.rs:777-790 consistency (fast == naive), extended to random + non-canonical states
     rng = np.random.default_rng(7)
     x = rng.integers(0, 1 << 64, size=(4096, 12), dtype=np.uint64)
+    # extreme halves for the add/shift MDS network (x86-64 form, poseidon_goldilocks.rs:217-248) against the
+    # plain circulant sums (poseidon.rs:178-198)
+    x[:64] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    x[64:128] = np.uint64(0xFFFFFFFF00000000)
+    x[128:192] = np.uint64(0x00000000FFFFFFFF)
+    x[192:256, ::2] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    x[192:256, 1::2] = 0
     a, b = oracle.poseidon(x), oracle.poseidon(x, naive=True)
     assert np.array_equal(a, b)
+    assert np.array_equal(a, oracle.poseidon(x, naive=2))
     xc = np.where(x >= np.uint64(P), x - np.uint64(P), x)
     assert np.array_equal(oracle.poseidon(xc), a)
     assert (a < np.uint64(P)).all()
