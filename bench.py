@@ -55,6 +55,17 @@ def ncu_traffic(width, lg_d, rate_bits, n_gpus):
     return int(e["dram_bytes_read"]) + int(e["dram_bytes_write"]), e.get("source", "profiles/leafhash_traffic.json")
 
 
+# thread-instructions per Poseidon permutation of the shipped k_hash_cols (ncu smsp__inst_executed x 32 / permutations, or the
+# static SASS count of its loop bodies when no capture of this build exists): profiles/leafhash_instr.json
+def leafhash_instr():
+    try:
+        with open(os.path.join(ROOT, "profiles", "leafhash_instr.json")) as f:
+            e = json.load(f)
+        return float(e["thread_instr_per_permutation"]), e.get("source", "profiles/leafhash_instr.json")
+    except (OSError, ValueError, KeyError):
+        return 17080.0, "profiles/r02_leafhash.md: 7.611e10 warp-instructions x 32 / (17 x 2^23) (round-2 build)"
+
+
 UNIT = "elems/s"
 
 
@@ -708,10 +719,10 @@ def run_ours(a):
                 "sm_mhz_used": sm_mhz}
     # issue-slot view of the same launch: instructions per permutation are a property of the compiled kernel (ncu
     # smsp__inst_executed x 32 / permutations of the shipped k_hash_cols, profiles/r02_leafhash.md); an SM issues 4 x 32 thread-instructions per clock
-    INSTR_PER_PERMUTATION = 17080.0   # profiles/r02_leafhash.md: 7.611e10 warp-instructions x 32 / (17 x 2^23)
+    INSTR_PER_PERMUTATION, instr_src = leafhash_instr()
     issue_peak = 148 * 128 * sm_mhz * 1e6
     int_pipe.update({
-        "thread_instr_per_permutation": INSTR_PER_PERMUTATION,
+        "thread_instr_per_permutation": INSTR_PER_PERMUTATION, "thread_instr_source": instr_src,
         "thread_instr_per_s": INSTR_PER_PERMUTATION * int_pipe["permutations_per_s"],
         "issue_peak_thread_instr_per_s": issue_peak,
         "issue_frac": INSTR_PER_PERMUTATION * int_pipe["permutations_per_s"] / issue_peak,

@@ -270,7 +270,7 @@ __device__ __forceinline__ void partial_round_d(uint64_t& x0, double (&dl)[12], 
 #if PCS_PARTIAL_SPLIT
     mds_net_d<true>(dl, yl);
     mds_net_d<true>(dh, yh);
-    x0 = gl::add_lc(sbox7(x0), rc);
+    x0 = gl::add_lc_p(sbox7(x0), rc);
     const double al = u32_as_double((uint32_t)x0), ah = u32_as_double((uint32_t)(x0 >> 32));
     // M[i][0] = MDS_MATRIX_CIRC[(12 - i) % 12] (+ MDS_MATRIX_DIAG[0] for i = 0)   poseidon_goldilocks.rs:24-25
     constexpr double COL0[12] = {25.0, 20.0, 34.0, 18.0, 39.0, 13.0, 13.0, 28.0, 2.0, 16.0, 41.0, 15.0};
@@ -280,7 +280,7 @@ __device__ __forceinline__ void partial_round_d(uint64_t& x0, double (&dl)[12], 
         dh[i] = fma(ah, COL0[i], yh[i]);
     }
 #else
-    x0 = gl::add_lc(sbox7(x0), rc);
+    x0 = gl::add_lc_p(sbox7(x0), rc);
     dl[0] = u32_as_double((uint32_t)x0);
     dh[0] = u32_as_double((uint32_t)(x0 >> 32));
     mds_net_d<false>(dl, yl);
@@ -336,7 +336,7 @@ template <bool CANON_OUT = true>
 __device__ __forceinline__ void poseidon12(uint64_t (&s)[12]) {
     using namespace pconst;
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl::add_lc(s[i], RC[i]);
+    for (int i = 0; i < 12; i++) s[i] = gl::add_lc_p(s[i], RC[i]);
 #if PCS_PARTIAL_FP64 && PCS_MDS_FP64
     // rounds 0..3 (full), 4..25 (partial, FP64-resident lanes), 26..29 (full): the two full-round groups share
     // ONE loop body (phase 0 and phase 1) so that the code stays small enough for the instruction cache
