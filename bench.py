@@ -727,7 +727,7 @@ def run_ours(a):
         "issue_peak_thread_instr_per_s": issue_peak,
         "issue_frac": INSTR_PER_PERMUTATION * int_pipe["permutations_per_s"] / issue_peak,
         "note": "the kernel's real ceiling: 64-bit modular arithmetic on 32-bit integer / FP64 pipes; measured pipe shares in "
-                "profiles/r01_poseidon_v3.md (FMA-heavy 51 % + FP64 47 % on one shared issue pipe, ALU 47 %)"})
+                "profiles/r01_poseidon_v3.md and profiles/r02_forms.md (FP64 50 % + the IMAD family on one shared issue pipe, ALU 36 %)"})
     kernels = {
         "lde_standalone": None if lde_alone is None else {
             "workload": f"standalone batched coset LDE: {w} polys x 2^{lg_d}, rate_bits {r} (pcs_coset_lde_dev, 2 launches)",

@@ -1,7 +1,7 @@
 // Element-wise Goldilocks field operations on the device (pcs_field_op): the device counterpart of the reference's
 // field-arithmetic grid test (field/src/prime_field_testing.rs:7-17,78-125, instantiated goldilocks_field.rs:405-411).
 // Every arithmetic routine of gl64.cuh that the kernels build on is reachable here, including BOTH 128-bit reductions
-// (reduce128 for the Poseidon S-boxes, reduce128_mad for the NTT butterflies), so the tests can compare each of them with
+// (reduce128 in the form the Poseidon S-boxes and the NTT butterflies are built with, and the multiply-add form reduce128_mad), so the tests can compare each of them with
 // big-int arithmetic on the boundary inputs {0..9, 2^31+-10, 2^32+-10, 2^63+-10, p-10..p-1, non-canonical values}.
 #include "common.cuh"
 #include "gl64.cuh"

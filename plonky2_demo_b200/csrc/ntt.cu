@@ -246,9 +246,10 @@ __device__ __forceinline__ uint64_t& tile_at(uint64_t* tile, uint32_t base_bytes
 
 // The butterfly's modular multiplication and addition.  PCS_NTT_MUL: 0 = the multiply-add reduction (gl::mul_mad, rounds 1-2:
 // 17 SASS), 2 = the wide reduction (gl::reduce128_wide: 14 SASS, the same number on the ALU pipe and three fewer on the IMAD
-// pipe).  PCS_NTT_ADD: 0 = gl::add_lc (7 SASS, 4 of them ALU), 1 = gl::add_lc_wide (5 SASS, all ALU).
+// pipe; LDE of 135 x 2^20 at rate 3: 20.16 -> 19.61 ms, profiles/r02_forms.md).  PCS_NTT_ADD: 0 = gl::add_lc (7 SASS, 4 of them
+// ALU), 1 = gl::add_lc_wide (5 SASS, all ALU: one more on the pipe that bounds the kernel, 128 registers and spills -- not used).
 #ifndef PCS_NTT_MUL
-#define PCS_NTT_MUL 0
+#define PCS_NTT_MUL 2
 #endif
 #ifndef PCS_NTT_ADD
 #define PCS_NTT_ADD 0

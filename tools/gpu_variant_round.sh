@@ -4,9 +4,10 @@
 # `-m gpu` parity suite on it, then the full bench line.
 mkdir -p gpurun_out
 rm -f gpurun_out/ab_*.json gpurun_out/ab_*.err
+python -c "import torch, numpy; print(torch.__version__)"   # page the image in once
 FLAGS="--steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-fri --no-from-values"
 for t in base d_n0 b_n2 h_n2; do
-  PCS_LIB=$PWD/build/variants/libpcs_$t.so timeout 30 python bench.py $FLAGS > gpurun_out/ab_$t.json 2> gpurun_out/ab_$t.err
+  PCS_LIB=$PWD/build/variants/libpcs_$t.so timeout 40 python bench.py $FLAGS > gpurun_out/ab_$t.json 2> gpurun_out/ab_$t.err
   echo "ab $t rc=$? $(date +%s)"
 done
 python tools/variant_pick.py > gpurun_out/variant_choice.json; cat gpurun_out/variant_choice.json

@@ -25,8 +25,10 @@ def main():
             rows[tag] = {"ok": False, "error": repr(e)}
     good = {t: r for t, r in rows.items() if r.get("ok")}
     choice = {"rows": rows, "hash": "base", "ntt": "n0", "tag": "base"}
-    if "base" in good:
-        base = good["base"]
+    # the round-2 build's phase times on this pool's B200s (profiles/r02_bench_1gpu_final.json) stand in when its own run is missing
+    base = good.get("base") or {"lde_ms": 20.17, "leaf_ms": 97.96, "node_ms": 5.98, "stored": True}
+    choice["base_used"] = base
+    if True:
         # hash form = first letter of the tag, NTT form = suffix
         best_h, best_h_ms = "base", base["leaf_ms"] + base["node_ms"]
         best_n, best_n_ms = "n0", base["lde_ms"]
