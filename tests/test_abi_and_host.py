@@ -198,6 +198,51 @@ def test_streaming_kernels_use_tma_bulk_copies(built_lib):
         assert "SYNCS" in body, kernel
 
 
+def _loop_bodies(sass, kernel):
+    """Instruction lists of the backward-branch loops of one kernel in a `cuobjdump -sass` listing."""
+    ins, on = [], False
+    for line in sass.split("\n"):
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            on = kernel in m.group(1)
+            continue
+        m = re.match(r"\s*/\*([0-9a-f]{4,6})\*/\s+(.*?);", line) if on else None
+        if m:
+            ins.append((int(m.group(1), 16), re.sub(r"^@!?U?P\d+\s+", "", m.group(2).strip())))
+    loops = []
+    for ad, t in ins:
+        m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d+,\s*)?(0x[0-9a-f]+)", t)
+        if m and int(m.group(1), 16) < ad:
+            loops.append([x for a, x in ins if int(m.group(1), 16) <= a <= ad])
+    return loops
+
+
+def test_leaf_hash_kernel_instruction_budget(built_lib):
+    """The reduction forms of csrc/gl64.cuh are chosen for what ptxas makes of them (profiles/r02_forms.md): the compiled
+    leaf-hash kernel must keep the instruction counts the measurements were taken with -- one full Poseidon round in ~1018
+    SASS instructions (1255 with the round 1-2 reductions), a partial-round pair in ~568 (610), five IMAD.WIDE per modular
+    multiplication, the FP64 MDS network intact, and no spills."""
+    import shutil
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    obj = os.path.join(ROOT, "plonky2_demo_b200", "build", "leaf_hash.o")
+    if not os.path.exists(cuobjdump) or not os.path.exists(obj):
+        pytest.skip("cuobjdump or the object file is not available")
+    sass = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True).stdout
+    loops = sorted((l for l in _loop_bodies(sass, "k_hash_colsE") if len(l) > 300), key=len)
+    assert len(loops) >= 2
+    pair, full = loops[0], loops[1]                      # the two innermost round loops; the outer loops contain them
+    count = lambda body, pre: sum(1 for t in body if t.split()[0].startswith(pre))
+    assert 500 <= len(pair) <= 585, len(pair)
+    assert 950 <= len(full) <= 1050, len(full)
+    assert count(full, "IMAD.WIDE") == 12 * 4 * 5        # 12 S-boxes x 4 multiplications x (4 product + 1 reduction)
+    assert count(full, "D") >= 190 and count(pair, "D") >= 400      # DADD / DFMA: the MDS layers run on the FP64 pipe
+    res = subprocess.run([cuobjdump, "-res-usage", obj], capture_output=True, text=True).stdout
+    usage = res[res.index("k_hash_colsE"):]
+    m = re.search(r"REG:(\d+) STACK:(\d+)", usage)
+    assert m and int(m.group(2)) == 0 and int(m.group(1)) <= 96, m and m.group(0)
+
+
 def test_c_abi_smoke_links_with_gcc_and_fails_loudly_without_a_gpu(tmp_path):
     """tests/c_abi_smoke.c is plain C: it must compile and link against libpcs.so with gcc (no nvcc, no Python), and on a
     box without a GPU the very first call fails with the engine's "no CPU fallback" message instead of computing anything."""
