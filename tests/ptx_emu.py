@@ -15,7 +15,7 @@ def preprocess(path, defines):
 
 
 def _in_string(src, start, pos):
-    return src.count('"', start, pos) % 2 == 1 and True
+    return src.count('"', start, pos) % 2 == 1
 
 
 def extract_asm(src, func):

@@ -28,22 +28,21 @@ def main():
     # the round-2 build's phase times on this pool's B200s (profiles/r02_bench_1gpu_final.json) stand in when its own run is missing
     base = good.get("base") or {"lde_ms": 20.17, "leaf_ms": 97.96, "node_ms": 5.98, "stored": True}
     choice["base_used"] = base
-    if True:
-        # hash form = first letter of the tag, NTT form = suffix
-        best_h, best_h_ms = "base", base["leaf_ms"] + base["node_ms"]
-        best_n, best_n_ms = "n0", base["lde_ms"]
-        for t, r in good.items():
-            if t == "base":
-                continue
-            h, n = t.split("_")
-            if r["leaf_ms"] + r["node_ms"] < 0.99 * best_h_ms:
-                best_h, best_h_ms = h, r["leaf_ms"] + r["node_ms"]
-            if n != "n0" and r["lde_ms"] < 0.995 * best_n_ms:
-                best_n, best_n_ms = n, r["lde_ms"]
-        if best_h == "base" and best_n != "n0":
-            best_n = "n0"          # no prebuilt library pairs the old hash forms with a new NTT form
-        tag = "base" if best_h == "base" else f"{best_h}_{best_n}"
-        choice.update(hash=best_h, ntt=best_n, tag=tag)
+    # hash form = first letter of the tag, NTT form = suffix
+    best_h, best_h_ms = "base", base["leaf_ms"] + base["node_ms"]
+    best_n, best_n_ms = "n0", base["lde_ms"]
+    for t, r in good.items():
+        if t == "base":
+            continue
+        h, n = t.split("_")
+        if r["leaf_ms"] + r["node_ms"] < 0.99 * best_h_ms:
+            best_h, best_h_ms = h, r["leaf_ms"] + r["node_ms"]
+        if n != "n0" and r["lde_ms"] < 0.995 * best_n_ms:
+            best_n, best_n_ms = n, r["lde_ms"]
+    if best_h == "base" and best_n != "n0":
+        best_n = "n0"          # no prebuilt library pairs the old hash forms with a new NTT form
+    tag = "base" if best_h == "base" else f"{best_h}_{best_n}"
+    choice.update(hash=best_h, ntt=best_n, tag=tag)
     lib = os.path.join(ROOT, "build", "variants", f"libpcs_{choice['tag']}.so")
     if not os.path.exists(lib):
         choice.update(tag="base")
